@@ -1,0 +1,165 @@
+/*
+ * ising_b200.h -- C ABI of libising_b200.so, the B200-native (sm_100a) checkerboard
+ * Metropolis engine that drops in for the hot path of NVIDIA/ising-gpu's optimized/
+ * program (reference files cited as optimized/main.cu:<line>).
+ *
+ * The reference has no FFI: its hot path sits behind `main()` of the cuIsing binary.
+ * The entry points below are what that main() does between option parsing and printing,
+ * one call per step of optimized/main.cu:1596-1925, so that a host written in any
+ * language (the C++ CLI in ising_gpu_b200/csrc/cuising_main.cpp, the ctypes mirror in
+ * ising_gpu_b200/engine.py, a cgo/JNI stub -- see INTEGRATION.md) can drive it.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative ISING_E* code otherwise; the message
+ *     is available from ising_last_error() (thread-local).  The library never calls exit():
+ *     the reference's "message on stderr + exit(EXIT_FAILURE)" policy (cudamacro.h:25-39)
+ *     is applied by the CLI, not here.
+ *   - plain pointers and sizes only; host buffers are caller-owned, device memory, streams,
+ *     events, peer mappings and tensor maps are library-owned.
+ *   - a context is driven by one host thread at a time (reference: single host thread,
+ *     main.cu:1764-1805).
+ *   - results are bit-identical to the reference for the same (X, rows, seed, temperature,
+ *     iteration number): the site -> (Philox subsequence, counter, lane) map of
+ *     main.cu:112-116, :514-515, :620-660 is kept; the device-internal packing is 1 bit/spin.
+ */
+#ifndef ISING_B200_H_
+#define ISING_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ISING_B200_ABI_VERSION 1
+
+#define ISING_MAX_DEVICES 256          /* MAX_GPU, optimized/main.cu:60 */
+#define ISING_DEFAULT_SEED 463463564571ull /* SEED_DEF, optimized/main.cu:63 */
+#define ISING_CRIT_TEMP 2.26918531421f /* CRIT_TEMP, optimized/main.cu:42 */
+
+enum {
+    ISING_OK = 0,
+    ISING_EINVAL = -1,  /* bad argument / lattice shape (main.cu:1412-1453)                 */
+    ISING_ECUDA = -2,   /* a CUDA runtime/driver call failed (CHECK_CUDA, cudamacro.h:25)    */
+    ISING_ENOPEER = -3, /* missing direct link between devices (main.cu:1531-1536)           */
+    ISING_ENOMEM = -4,
+    ISING_ESTATE = -5   /* call not valid in this state (e.g. halo access on a 1-slab ctx)   */
+};
+
+enum { ISING_BLACK = 0, ISING_WHITE = 1 }; /* enum {C_BLACK, C_WHITE}, main.cu:80 */
+
+typedef struct ising_ctx ising_ctx;
+
+/* Configuration = the scalars main() derives from its options (main.cu:1245-1283,
+ * :1395-1471).  Zero-initialise, then fill. */
+typedef struct ising_cfg {
+    int32_t X;            /* -x: lattice columns, black+white; multiple of 2048 (main.cu:1412) */
+    int32_t Y;            /* -y: lattice rows PER DEVICE; multiple of 16 (main.cu:1417)        */
+    int32_t ndev;         /* -d: devices driven by this context (>=1)                          */
+    int32_t first_device; /* CUDA ordinal of device 0 of the context (reference: always 0)      */
+    uint64_t seed;        /* -s (main.cu:1329)                                                  */
+    float temp;           /* absolute temperature (main.cu:1465-1471 resolves -a / -t)          */
+    int32_t xsl;          /* --xsl sub-lattice columns, 0 = disabled (main.cu:1423-1463)        */
+    int32_t ysl;          /* --ysl sub-lattice rows,    0 = disabled                            */
+    /* Placement of this context's slabs inside a larger lattice that is spread over several
+     * processes (one process per GPU under torchrun).  The reference is single-process
+     * (devid = 0..ndev-1, main.cu:1764); slab s of the global lattice is what the reference
+     * calls devid.  slab_count == 0 means "this context is the whole lattice". */
+    int32_t slab_first;   /* global slab index of this context's device 0                      */
+    int32_t slab_count;   /* slabs in the global lattice (0 -> ndev)                            */
+    int32_t flags;        /* ISING_F_* */
+    int32_t reserved[5];
+} ising_cfg;
+
+enum {
+    ISING_F_NO_PEER_COPY = 1 /* multi-slab context whose ghost rows are filled by the caller
+                                (NCCL send/recv or IPC stores), not by the library           */
+};
+
+/* ---- lifetime --------------------------------------------------------------------------
+ * ising_create replaces main.cu:1481-1537 (device checks, peer enabling) and :1596-1706
+ * (allocations, acceptance table).  ising_destroy replaces :1900-1925 (without
+ * cudaDeviceReset: the process may hold other CUDA state). */
+int ising_create(const ising_cfg* cfg, ising_ctx** out);
+int ising_destroy(ising_ctx* ctx);
+const char* ising_last_error(void);
+int ising_abi_version(void);
+
+/* Use caller-provided streams (e.g. torch.cuda.current_stream().cuda_stream) instead of the
+ * context's own; stream is a cudaStream_t passed as void*.  dev = index inside the context. */
+int ising_set_stream(ising_ctx* ctx, int dev, void* stream);
+
+/* ---- the hot path ----------------------------------------------------------------------*/
+/* latticeInit_k x2 (main.cu:1708-1726): random spins from Philox step it=0. */
+int ising_init_lattice(ising_ctx* ctx);
+
+/* One colour half-sweep on every device of the context: spinUpdateV_2D_k<COLOR> with
+ * iteration number `it` (main.cu:1766-1777 / :1787-1798; it = j+1 for sweep j) followed by
+ * the halo push of that colour's boundary rows.  Asynchronous. */
+int ising_update_color(ising_ctx* ctx, int color, int it);
+
+/* n full sweeps, iteration numbers first_it .. first_it+n-1 (the reference's loop
+ * main.cu:1763-1805 uses first_it = 1).  Asynchronous; ising_sync waits. */
+int ising_sweeps(ising_ctx* ctx, int first_it, int n);
+int ising_sync(ising_ctx* ctx);
+
+/* Same as ising_sweeps + ising_sync, bracketed by CUDA events on the launching stream(s)
+ * (main.cu:1758, :1863, :1879); *ms = elapsed device time, max over the context's devices. */
+int ising_sweeps_timed(ising_ctx* ctx, int first_it, int n, float* ms);
+
+/* Rebuild the acceptance table for a new temperature (main.cu:1848-1859). */
+int ising_set_temperature(ising_ctx* ctx, float temp);
+
+/* ---- observables -----------------------------------------------------------------------*/
+/* countSpins / getMagn_k (main.cu:831-868): #up and #down over the context's slabs. */
+int ising_count_spins(ising_ctx* ctx, uint64_t* up, uint64_t* down);
+/* Sum over nearest-neighbour bonds of s_i*s_j (s = +-1) for the context's slabs; energy per
+ * site = -bond_sum / (rows*X).  (The reference exposes this only via -c, main.cu:1129-1135.) */
+int ising_bond_sum(ising_ctx* ctx, int64_t* bond_sum);
+
+/* ---- lattice transfer ------------------------------------------------------------------*/
+/* Reference storage format of one device's slab (main.cu:1160-1175): Y*X/32 uint64 words per
+ * colour, 16 spins per word, nibble k = colour-column 16*j+k, bit 0 of the nibble = spin. */
+int ising_export_ref_layout(ising_ctx* ctx, int dev, uint64_t* black, uint64_t* white);
+int ising_import_ref_layout(ising_ctx* ctx, int dev, const uint64_t* black, const uint64_t* white);
+/* Device packing: Y*X/64 uint32 words per colour, bit b of word w = colour-column 32*w+b. */
+int ising_export_bits(ising_ctx* ctx, int dev, uint32_t* black, uint32_t* white);
+int ising_import_bits(ising_ctx* ctx, int dev, const uint32_t* black, const uint32_t* white);
+/* dumpLattice (main.cu:1140-1209): writes "<prefix><dev>.txt" for every device of the context. */
+int ising_dump_lattice(ising_ctx* ctx, const char* prefix);
+
+/* End-to-end convenience used by bench.py's e2e leg: upload both colour planes of device 0
+ * from host (bit packing), run n sweeps starting at first_it, download the planes and the
+ * spin counts.  Everything (H2D, kernels, D2H) happens inside the call. */
+int ising_run_from_host(ising_ctx* ctx, const uint32_t* black_in, const uint32_t* white_in,
+                        int first_it, int n, uint32_t* black_out, uint32_t* white_out,
+                        uint64_t* up, uint64_t* down);
+
+/* ---- multi-process slabs (one process per GPU) ------------------------------------------
+ * Device pointer and byte length of one row of a colour plane.  row = -1 is the ghost row
+ * above the slab, row = Y the ghost row below it, 0..Y-1 the slab's own rows.  The caller
+ * fills ghost rows (from the neighbouring slabs' rows Y-1 / 0) between colour updates. */
+int ising_row_ptr(ising_ctx* ctx, int dev, int color, int row, void** dptr, size_t* nbytes);
+/* Update only the tile rows that touch the slab edge (first/last 16 rows) or only the rest;
+ * lets the caller overlap the halo exchange with the interior (see engine.SlabEngine). */
+enum { ISING_PART_ALL = 0, ISING_PART_EDGES = 1, ISING_PART_INTERIOR = 2 };
+int ising_update_color_part(ising_ctx* ctx, int dev, int color, int it, int part, void* stream);
+
+/* ---- introspection used by tests and bench ----------------------------------------------*/
+/* Number of 32-bit Philox outputs x accepted by `uniform(x) <= p` (strict = 0) or
+ * `uniform(x) < p` (strict = 1), uniform(x) = x*2^-32 + 2^-33 in float (curand_uniform).
+ * Host-only arithmetic: valid without a GPU.  Range 0 .. 2^32. */
+uint64_t ising_accept_count(float p, int strict);
+/* The 5 acceptance probabilities by number of ALIGNED neighbours a = 0..4 for temperature
+ * temp, i.e. exp_h[1][a] of main.cu:1683-1697 (host expf). */
+void ising_accept_table(float temp, float out[5]);
+/* kernels launched by this context since creation (bench.py's gpu_launches). */
+uint64_t ising_launch_count(const ising_ctx* ctx);
+/* name of the update kernel variant in use, for logs */
+const char* ising_kernel_name(const ising_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ISING_B200_H_ */

@@ -1,0 +1,390 @@
+// kernels.cu -- sm_100a kernels of the checkerboard Metropolis hot path.
+//
+// Replaces (reference, optimized/main.cu): latticeInit_k :92-151, loadTile :380-461,
+// spinUpdateV_2D_k :463-670, getMagn_k :702-734.  Not a port: spins are 1 bit each (32 sites
+// per word), the source-colour tile and its halo arrive through TMA (cp.async.bulk.tensor)
+// boxes whose coordinates carry the periodic wrap, the Philox counter schedule is folded per
+// launch/per thread (philox_map.h), and acceptance is an integer compare on the raw Philox
+// output that is shifted into bit masks through the carry flag -- no int->float conversion,
+// no table lookup, no per-spin extraction.  What is kept is the contract: which Philox
+// output decides which site, and the float acceptance table it is compared against.
+#include "kernels.cuh"
+
+namespace ising {
+
+// ------------------------------------------------------------------------------------------
+// small PTX wrappers (mbarrier + TMA), sm_90+/sm_100a
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int x, int y, uint64_t* bar)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+            smem_u32(dst)),
+        "l"(map), "r"(x), "r"(y), "r"(smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, int x, int y, const void* src)
+{
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(map), "r"(x),
+                 "r"(y), "r"(smem_u32(src))
+                 : "memory");
+}
+__device__ __forceinline__ void tma_store_commit_wait()
+{
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// acc = 2*acc + (x > thr): the compare lands in the carry flag and is shifted in by the
+// add-with-carry (IADD3 + IADD3.X / IMAD.X in SASS).  Rejected sites accumulate as 1 bits.
+__device__ __forceinline__ void shift_in_reject(uint32_t& acc, uint32_t x, uint32_t thr)
+{
+    asm("{\n"
+        ".reg .u32 t;\n"
+        "sub.cc.u32 t, %2, %1;\n"
+        "addc.u32 %0, %0, %0;\n"
+        "}\n"
+        : "+r"(acc)
+        : "r"(x), "r"(thr));
+}
+
+// Reject masks of one 32-site word: 8 Philox calls, outputs x,y,z,w -> bits 2q, 16+2q, 2q+1,
+// 17+2q.  Calls run q = 7..0 so that shifting in z then x (w then y) leaves bit k of the
+// 16-bit accumulators == site k.
+template <int NTHR, int J>
+__device__ __forceinline__ void word_reject_masks(const ThreadConsts& tc, const StepTables& st, uint32_t thrA,
+                                                  uint32_t thrB, uint32_t& rejA, uint32_t& rejB)
+{
+    uint32_t a_lo = 0, a_hi = 0, b_lo = 0, b_hi = 0;
+#pragma unroll
+    for (int q = 7; q >= 0; q--) {
+        const int cl = 8 * J + q;
+        uint32_t o[4];
+        philox_fast(tc, st.a[cl], st.b[cl], st.d[cl], st.k0, st.k1, o);
+        shift_in_reject(a_lo, o[2], thrA);
+        shift_in_reject(a_lo, o[0], thrA);
+        shift_in_reject(a_hi, o[3], thrA);
+        shift_in_reject(a_hi, o[1], thrA);
+        if (NTHR > 1) {
+            shift_in_reject(b_lo, o[2], thrB);
+            shift_in_reject(b_lo, o[0], thrB);
+            shift_in_reject(b_hi, o[3], thrB);
+            shift_in_reject(b_hi, o[1], thrB);
+        }
+    }
+    rejA = __byte_perm(a_lo, a_hi, 0x5410);
+    rejB = (NTHR > 1) ? __byte_perm(b_lo, b_hi, 0x5410) : 0u;
+}
+
+// Flip mask of one word from its own spins, the four neighbour words and the reject masks.
+template <bool FAST>
+__device__ __forceinline__ uint32_t flip_mask(uint32_t me, uint32_t up, uint32_t dn, uint32_t ct, uint32_t sd,
+                                              uint32_t rejA, uint32_t rejB, const AcceptRule& r)
+{
+    // d_k = neighbour_k ^ me = 1 where anti-aligned; (g,p) and (g2,p2) are the 2-bit sums of pairs
+    const uint32_t p = up ^ dn, g = (up ^ me) & (dn ^ me);
+    const uint32_t p2 = ct ^ sd, g2 = (ct ^ me) & (sd ^ me);
+    if (FAST) {
+        const uint32_t none = ~(p | g | p2 | g2);       // 4 aligned: dE = +8 -> slot B
+        const uint32_t one = (p ^ p2) & ~(g | g2);      // 3 aligned: dE = +4 -> slot A
+        return ~((one & rejA) | (none & rejB));          // everything else always flips
+    } else {
+        const uint32_t c = p & p2;
+        const uint32_t b0 = p ^ p2, b1 = g ^ g2 ^ c, b2 = g & g2;   // b = number anti-aligned
+        const uint32_t accA = ~rejA, accB = ~rejB;
+        uint32_t cls[5];
+        cls[0] = ~(b0 | b1 | b2); cls[1] = b0 & ~b1; cls[2] = ~b0 & b1; cls[3] = b0 & b1; cls[4] = b2;
+        uint32_t f = 0;
+#pragma unroll
+        for (int b = 0; b < 5; b++) f |= cls[b] & (r.always[b] | (r.selA[b] & accA) | (r.selB[b] & accB));
+        return f;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Colour half-sweep.  One CTA = one 16 x 32-word tile, one thread = one reference thread id
+// (words tx and tx+16 of row ty).  Six TMA boxes per tile: source centre, source row above,
+// source row below, 16-byte source boxes left and right, and the tile's own spins; one TMA
+// store writes the tile back.
+// ------------------------------------------------------------------------------------------
+template <bool FAST>
+__global__ void __launch_bounds__(UPDATE_THREADS, 4)
+update_color_kernel(const __grid_constant__ CUtensorMap src_tile, const __grid_constant__ CUtensorMap src_row,
+                    const __grid_constant__ CUtensorMap src_side, const __grid_constant__ CUtensorMap dst_tile,
+                    const __grid_constant__ UpdateParams p)
+{
+    __shared__ alignas(128) uint32_t sV[(TH + 2) * TW];   // rows: above, 16 centre rows, below
+    __shared__ alignas(128) uint32_t sL[TH * SIDE_W];
+    __shared__ alignas(128) uint32_t sR[TH * SIDE_W];
+    __shared__ alignas(128) uint32_t sD[TH * TW];         // own colour, updated in place
+    __shared__ alignas(8) uint64_t bar;
+
+    const int tile_row = p.edges_mode ? (blockIdx.y == 0 ? p.tile_row0 : p.tile_row_alt) : p.tile_row0 + (int)blockIdx.y;
+    const int x0 = blockIdx.x * TW;       // first word of the tile in the row
+    const int y0 = tile_row * TH;         // first local row of the tile
+
+    if (threadIdx.x == 0) {
+        mbar_init(&bar, 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int ytop, ybot;
+        if (p.yperiod > 0) {
+            ytop = (y0 % p.yperiod == 0) ? y0 + p.yperiod - 1 : y0 - 1;
+            ybot = ((y0 + TH) % p.yperiod == 0) ? y0 + TH - p.yperiod : y0 + TH;
+        } else {
+            ytop = y0 - 1;    // ghost row above the slab when y0 == 0
+            ybot = y0 + TH;   // ghost row below the slab when y0 + TH == rows
+        }
+        const int xl = (x0 % p.xperiod == 0) ? x0 + p.xperiod - 1 : x0 - 1;
+        const int xr = ((x0 + TW) % p.xperiod == 0) ? x0 + TW - p.xperiod : x0 + TW;
+        constexpr uint32_t bytes = ((TH + 2) * TW + 2 * TH * SIDE_W + TH * TW) * 4;
+        mbar_expect_tx(&bar, bytes);
+        // allocation row = local row + 1 (row 0 of the allocation is the upper ghost row)
+        tma_load_2d(sV + TW, &src_tile, x0, y0 + 1, &bar);
+        tma_load_2d(sV, &src_row, x0, ytop + 1, &bar);
+        tma_load_2d(sV + (TH + 1) * TW, &src_row, x0, ybot + 1, &bar);
+        tma_load_2d(sL, &src_side, xl - (SIDE_W - 1), y0 + 1, &bar);
+        tma_load_2d(sR, &src_side, xr, y0 + 1, &bar);
+        tma_load_2d(sD, &dst_tile, x0, y0 + 1, &bar);
+    }
+
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    const uint32_t grow = p.grow0 + (uint32_t)(y0 + ty);
+    const uint32_t tid = ref_tid(grow, (uint32_t)(x0 + tx), p.grid_x);
+    const ThreadConsts tc = make_thread_consts(tid, p.st.x1, p.st.k1r3);
+    // side neighbour is at colour-column m-1 ("readBack", main.cu:542) or m+1
+    const bool read_back = (p.color == 0) ? !(grow & 1u) : (grow & 1u);
+
+    uint32_t rejA[2], rejB[2];
+    if (FAST || p.rule.selB[0] | p.rule.selB[1] | p.rule.selB[2] | p.rule.selB[3] | p.rule.selB[4]) {
+        word_reject_masks<2, 0>(tc, p.st, p.rule.thrA, p.rule.thrB, rejA[0], rejB[0]);
+        word_reject_masks<2, 1>(tc, p.st, p.rule.thrA, p.rule.thrB, rejA[1], rejB[1]);
+    } else {
+        word_reject_masks<1, 0>(tc, p.st, p.rule.thrA, p.rule.thrB, rejA[0], rejB[0]);
+        word_reject_masks<1, 1>(tc, p.st, p.rule.thrA, p.rule.thrB, rejA[1], rejB[1]);
+    }
+
+    mbar_wait(&bar, 0);
+
+#pragma unroll
+    for (int j = 0; j < 2; j++) {
+        const int w = tx + 16 * j;
+        const uint32_t up = sV[ty * TW + w];
+        const uint32_t ct = sV[(ty + 1) * TW + w];
+        const uint32_t dn = sV[(ty + 2) * TW + w];
+        const uint32_t me = sD[ty * TW + w];
+        uint32_t sd;
+        if (read_back) {
+            const uint32_t prev = (w == 0) ? sL[ty * SIDE_W + SIDE_W - 1] : sV[(ty + 1) * TW + w - 1];
+            sd = __funnelshift_l(prev, ct, 1);    // (ct << 1) | (prev >> 31)
+        } else {
+            const uint32_t next = (w == TW - 1) ? sR[ty * SIDE_W] : sV[(ty + 1) * TW + w + 1];
+            sd = __funnelshift_r(ct, next, 1);    // (ct >> 1) | (next << 31)
+        }
+        sD[ty * TW + w] = me ^ flip_mask<FAST>(me, up, dn, ct, sd, rejA[j], rejB[j], p.rule);
+    }
+
+    fence_proxy_async_smem();     // generic-proxy writes to sD -> visible to the TMA store
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        tma_store_2d(&dst_tile, x0, y0 + 1, sD);
+        tma_store_commit_wait();
+    }
+}
+
+void launch_update(const CUtensorMap& src_tile, const CUtensorMap& src_row, const CUtensorMap& src_side,
+                   const CUtensorMap& dst_tile, const UpdateParams& p, int tiles_x, int tiles_y, cudaStream_t stream)
+{
+    const dim3 grid((unsigned)tiles_x, (unsigned)tiles_y);
+    if (p.rule.fast)
+        update_color_kernel<true><<<grid, UPDATE_THREADS, 0, stream>>>(src_tile, src_row, src_side, dst_tile, p);
+    else
+        update_color_kernel<false><<<grid, UPDATE_THREADS, 0, stream>>>(src_tile, src_row, src_side, dst_tile, p);
+}
+
+const char* update_kernel_name(int fast)
+{
+    return fast ? "update_color_kernel<fast: 2 integer thresholds, TMA 16x32-word tiles, 1 bit/spin>"
+                : "update_color_kernel<generic acceptance rule, TMA 16x32-word tiles, 1 bit/spin>";
+}
+
+// ------------------------------------------------------------------------------------------
+// Lattice init (latticeInit_k): spin = (uniform < 0.5f) <=> x <= thr_half.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(UPDATE_THREADS) init_kernel(uint32_t* __restrict__ plane /* local row 0 */,
+                                                             const __grid_constant__ InitParams p)
+{
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    const int x0 = blockIdx.x * TW;
+    const int row = blockIdx.y * TH + ty;
+    const uint32_t grow = p.grow0 + (uint32_t)row;
+    const uint32_t tid = ref_tid(grow, (uint32_t)(x0 + tx), p.grid_x);
+    const ThreadConsts tc = make_thread_consts(tid, p.st.x1, p.st.k1r3);
+    uint32_t rej0, rej1, unused;
+    word_reject_masks<1, 0>(tc, p.st, p.thr_half, 0u, rej0, unused);
+    word_reject_masks<1, 1>(tc, p.st, p.thr_half, 0u, rej1, unused);
+    uint32_t* r = plane + (size_t)row * p.pitch + x0 + tx;
+    r[0] = ~rej0;
+    r[16] = ~rej1;
+}
+
+void launch_init(uint32_t* plane, const InitParams& p, cudaStream_t stream)
+{
+    const dim3 grid((unsigned)(p.pitch / TW), (unsigned)(p.rows / TH));
+    init_kernel<<<grid, UPDATE_THREADS, 0, stream>>>(plane, p);
+}
+
+// ------------------------------------------------------------------------------------------
+// Observables
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long block_sum_u64(unsigned long long v)
+{
+    __shared__ unsigned long long sh[32];
+#pragma unroll
+    for (int o = 16; o; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (lane == 0) sh[wid] = v;
+    __syncthreads();
+    if (wid == 0) {
+        v = (lane < (int)(blockDim.x >> 5)) ? sh[lane] : 0ull;
+#pragma unroll
+        for (int o = 16; o; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    }
+    return v;
+}
+
+__global__ void __launch_bounds__(256) count_kernel(const uint4* __restrict__ plane, size_t n4,
+                                                   unsigned long long* __restrict__ counts)
+{
+    unsigned long long acc = 0;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+        const uint4 v = plane[i];
+        acc += __popc(v.x) + __popc(v.y) + __popc(v.z) + __popc(v.w);
+    }
+    acc = block_sum_u64(acc);
+    if (threadIdx.x == 0) atomicAdd(counts, acc);
+}
+
+void launch_count(const uint32_t* plane, int rows, int pitch, unsigned long long* counts, cudaStream_t stream)
+{
+    const size_t n4 = (size_t)rows * pitch / 4;
+    const int blocks = (int)((n4 + 255) / 256 < 148 * 8 ? (n4 + 255) / 256 : 148 * 8);
+    count_kernel<<<blocks, 256, 0, stream>>>(reinterpret_cast<const uint4*>(plane), n4, counts);
+}
+
+// Number of unequal nearest-neighbour pairs: every bond joins one black and one white site, so
+// visiting the four white neighbours of every black site counts each bond once.
+__global__ void __launch_bounds__(256) bond_differ_kernel(const uint32_t* __restrict__ black,
+                                                         const uint32_t* __restrict__ white, int rows, int pitch,
+                                                         int yperiod, int xperiod, uint32_t grow0,
+                                                         unsigned long long* __restrict__ counts)
+{
+    unsigned long long acc = 0;
+    const size_t n = (size_t)rows * pitch;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const int r = (int)(i / pitch), w = (int)(i % pitch);
+        int ru, rd;
+        if (yperiod > 0) {
+            ru = (r % yperiod == 0) ? r + yperiod - 1 : r - 1;
+            rd = ((r + 1) % yperiod == 0) ? r + 1 - yperiod : r + 1;
+        } else {
+            ru = r - 1; rd = r + 1;      // ghost rows
+        }
+        const int wl = (w % xperiod == 0) ? w + xperiod - 1 : w - 1;
+        const int wr = ((w + 1) % xperiod == 0) ? w + 1 - xperiod : w + 1;
+        const uint32_t me = black[(ptrdiff_t)r * pitch + w];
+        const uint32_t up = white[(ptrdiff_t)ru * pitch + w];
+        const uint32_t dn = white[(ptrdiff_t)rd * pitch + w];
+        const uint32_t ct = white[(ptrdiff_t)r * pitch + w];
+        const bool read_back = !((grow0 + (uint32_t)r) & 1u);
+        const uint32_t sd = read_back ? __funnelshift_l(white[(ptrdiff_t)r * pitch + wl], ct, 1)
+                                      : __funnelshift_r(ct, white[(ptrdiff_t)r * pitch + wr], 1);
+        acc += __popc(me ^ up) + __popc(me ^ dn) + __popc(me ^ ct) + __popc(me ^ sd);
+    }
+    acc = block_sum_u64(acc);
+    if (threadIdx.x == 0) atomicAdd(counts, acc);
+}
+
+void launch_bond_differ(const uint32_t* black, const uint32_t* white, int rows, int pitch, int yperiod, int xperiod,
+                        uint32_t grow0, unsigned long long* counts, cudaStream_t stream)
+{
+    bond_differ_kernel<<<148 * 8, 256, 0, stream>>>(black, white, rows, pitch, yperiod, xperiod, grow0, counts);
+}
+
+// ------------------------------------------------------------------------------------------
+// Conversion to / from the reference's 4-bit storage (main.cu:1160-1175): 16 spins per uint64,
+// nibble k = site 16*j + k.  One 32-site word <-> two uint64.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long spread16(uint32_t h)
+{
+    unsigned long long x = h & 0xffffu;
+    x = (x | (x << 24)) & 0x000000ff000000ffull;
+    x = (x | (x << 12)) & 0x000f000f000f000full;
+    x = (x | (x << 6)) & 0x0303030303030303ull;
+    x = (x | (x << 3)) & 0x1111111111111111ull;
+    return x;
+}
+__device__ __forceinline__ uint32_t gather16(unsigned long long x)
+{
+    x &= 0x1111111111111111ull;
+    x = (x | (x >> 3)) & 0x0303030303030303ull;
+    x = (x | (x >> 6)) & 0x000f000f000f000full;
+    x = (x | (x >> 12)) & 0x000000ff000000ffull;
+    x = (x | (x >> 24)) & 0xffffull;
+    return (uint32_t)x;
+}
+
+__global__ void __launch_bounds__(256) to_ref_kernel(const uint32_t* __restrict__ plane, size_t n,
+                                                    ulonglong2* __restrict__ out)
+{
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const uint32_t v = plane[i];
+        out[i] = make_ulonglong2(spread16(v), spread16(v >> 16));
+    }
+}
+__global__ void __launch_bounds__(256) from_ref_kernel(const ulonglong2* __restrict__ in, size_t n,
+                                                      uint32_t* __restrict__ plane)
+{
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const ulonglong2 v = in[i];
+        plane[i] = gather16(v.x) | (gather16(v.y) << 16);
+    }
+}
+
+void launch_to_ref(const uint32_t* plane, int rows, int pitch, unsigned long long* out, cudaStream_t stream)
+{
+    to_ref_kernel<<<148 * 8, 256, 0, stream>>>(plane, (size_t)rows * pitch, reinterpret_cast<ulonglong2*>(out));
+}
+void launch_from_ref(const unsigned long long* in, int rows, int pitch, uint32_t* plane, cudaStream_t stream)
+{
+    from_ref_kernel<<<148 * 8, 256, 0, stream>>>(reinterpret_cast<const ulonglong2*>(in), (size_t)rows * pitch, plane);
+}
+
+}  // namespace ising

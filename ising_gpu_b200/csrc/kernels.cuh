@@ -1,0 +1,64 @@
+// kernels.cuh -- parameter blocks shared by kernels.cu (device) and ising_api.cu (host).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "philox_map.h"
+
+namespace ising {
+
+// Tile of one CTA: 16 rows x 32 words (32 sites each) of the colour being updated == one
+// thread block of the reference launch (optimized/main.cu:1547-1550), so that one thread
+// owns exactly one reference thread id and its 16 Philox calls.
+constexpr int TH = 16;
+constexpr int TW = 32;
+constexpr int SIDE_W = 4;           // 16-byte halo box left/right of the tile (TMA minimum)
+constexpr int UPDATE_THREADS = 256;
+
+// Acceptance rule in integer form.  For b = number of ANTI-aligned neighbours (0..4, i.e.
+// 4-b aligned) a spin flips iff  always[b] | (selA[b] & x<=thrA) | (selB[b] & x<=thrB),
+// x = the site's 32-bit Philox output.  Built on the host from exp_h (main.cu:1683-1697).
+struct AcceptRule {
+    uint32_t thrA, thrB;
+    uint32_t always[5], selA[5], selB[5];   // 0 or 0xffffffff
+    int fast;   // 1 when always = {0,0,1,1,1}, selA = b==1, selB = b==0 (every T > ~0.37)
+};
+
+struct UpdateParams {
+    StepTables st;
+    AcceptRule rule;
+    uint32_t grid_x;        // X/2048 = reference gridDim.x
+    uint32_t grow0;         // global row of this slab's local row 0 (devid*Y)
+    int tile_row0;          // first tile row handled by blockIdx.y == 0
+    int tile_row_alt;       // edges mode: tile row handled by blockIdx.y == 1
+    int edges_mode;
+    int rows;               // local rows Y
+    int yperiod;            // vertical wrap period in rows inside the slab; 0 = ghost rows
+    int xperiod;            // horizontal wrap period in words
+    int color;
+};
+
+struct InitParams {
+    StepTables st;
+    uint32_t thr_half;      // spin = 1 iff x <= thr_half  (uniform < 0.5f, main.cu:133)
+    uint32_t grid_x;
+    uint32_t grow0;
+    int rows;
+    int pitch;              // words per row
+};
+
+void launch_update(const CUtensorMap& src_tile, const CUtensorMap& src_row, const CUtensorMap& src_side,
+                   const CUtensorMap& dst_tile, const UpdateParams& p, int tiles_x, int tiles_y,
+                   cudaStream_t stream);
+void launch_init(uint32_t* plane, const InitParams& p, cudaStream_t stream);
+// counts[0] += popcount over rows 0..rows-1 of the plane
+void launch_count(const uint32_t* plane, int rows, int pitch, unsigned long long* counts, cudaStream_t stream);
+// counts[0] += number of unequal nearest-neighbour pairs seen from the black sites
+void launch_bond_differ(const uint32_t* black, const uint32_t* white, int rows, int pitch, int yperiod,
+                        int xperiod, uint32_t grow0, unsigned long long* counts, cudaStream_t stream);
+void launch_to_ref(const uint32_t* plane, int rows, int pitch, unsigned long long* out, cudaStream_t stream);
+void launch_from_ref(const unsigned long long* in, int rows, int pitch, uint32_t* plane, cudaStream_t stream);
+const char* update_kernel_name(int fast);
+
+}  // namespace ising

@@ -1,0 +1,255 @@
+"""ctypes mirror of include/ising_b200.h.
+
+``IsingEngine`` follows the step order of the reference's main() (optimized/main.cu:1596-1925):
+create -> init_lattice -> [sweeps | count_spins | dump]* -> destroy, with the same argument
+meaning as the reference's options (-x, -y per device, -d, -s, -t/-a, --xsl/--ysl).
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+DEFAULT_SEED = 463463564571            # SEED_DEF, optimized/main.cu:63
+CRIT_TEMP = np.float32(2.26918531421)  # CRIT_TEMP, optimized/main.cu:42
+ALPHA_DEF = np.float32(0.1)            # ALPHA_DEF, optimized/main.cu:43
+
+BLACK, WHITE = 0, 1
+PART_ALL, PART_EDGES, PART_INTERIOR = 0, 1, 2
+F_NO_PEER_COPY = 1
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+
+class IsingError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("ising_b200 error %d: %s" % (code, msg))
+        self.code = code
+
+
+class _Cfg(C.Structure):
+    _fields_ = [("X", C.c_int32), ("Y", C.c_int32), ("ndev", C.c_int32), ("first_device", C.c_int32),
+                ("seed", C.c_uint64), ("temp", C.c_float), ("xsl", C.c_int32), ("ysl", C.c_int32),
+                ("slab_first", C.c_int32), ("slab_count", C.c_int32), ("flags", C.c_int32),
+                ("reserved", C.c_int32 * 5)]
+
+
+def lib_path():
+    return os.path.join(_HERE, "libising_b200.so")
+
+
+def load_library():
+    """Load libising_b200.so (built in-tree by `make` / __graft_entry__.build()).  No fallback."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    p = lib_path()
+    if not os.path.exists(p):
+        raise IsingError(-100, "%s not built: run `make` (or __graft_entry__.build()) first" % p)
+    L = C.CDLL(p)
+    vp, u64p, u32p = C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint32)
+    sig = {
+        "ising_create": ([C.POINTER(_Cfg), C.POINTER(vp)], C.c_int),
+        "ising_destroy": ([vp], C.c_int),
+        "ising_last_error": ([], C.c_char_p),
+        "ising_abi_version": ([], C.c_int),
+        "ising_set_stream": ([vp, C.c_int, vp], C.c_int),
+        "ising_init_lattice": ([vp], C.c_int),
+        "ising_update_color": ([vp, C.c_int, C.c_int], C.c_int),
+        "ising_sweeps": ([vp, C.c_int, C.c_int], C.c_int),
+        "ising_sync": ([vp], C.c_int),
+        "ising_sweeps_timed": ([vp, C.c_int, C.c_int, C.POINTER(C.c_float)], C.c_int),
+        "ising_set_temperature": ([vp, C.c_float], C.c_int),
+        "ising_count_spins": ([vp, u64p, u64p], C.c_int),
+        "ising_bond_sum": ([vp, C.POINTER(C.c_int64)], C.c_int),
+        "ising_export_ref_layout": ([vp, C.c_int, vp, vp], C.c_int),
+        "ising_import_ref_layout": ([vp, C.c_int, vp, vp], C.c_int),
+        "ising_export_bits": ([vp, C.c_int, vp, vp], C.c_int),
+        "ising_import_bits": ([vp, C.c_int, vp, vp], C.c_int),
+        "ising_dump_lattice": ([vp, C.c_char_p], C.c_int),
+        "ising_run_from_host": ([vp, vp, vp, C.c_int, C.c_int, vp, vp, u64p, u64p], C.c_int),
+        "ising_row_ptr": ([vp, C.c_int, C.c_int, C.c_int, C.POINTER(vp), C.POINTER(C.c_size_t)], C.c_int),
+        "ising_update_color_part": ([vp, C.c_int, C.c_int, C.c_int, C.c_int, vp], C.c_int),
+        "ising_accept_count": ([C.c_float, C.c_int], C.c_uint64),
+        "ising_accept_table": ([C.c_float, C.POINTER(C.c_float)], None),
+        "ising_launch_count": ([vp], C.c_uint64),
+        "ising_kernel_name": ([vp], C.c_char_p),
+    }
+    for name, (args, res) in sig.items():
+        fn = getattr(L, name)      # AttributeError here = header and library out of sync
+        fn.argtypes, fn.restype = args, res
+    _LIB = L
+    return L
+
+
+EXPORTED_SYMBOLS = ("ising_create ising_destroy ising_last_error ising_abi_version ising_set_stream "
+                    "ising_init_lattice ising_update_color ising_sweeps ising_sync ising_sweeps_timed "
+                    "ising_set_temperature ising_count_spins ising_bond_sum ising_export_ref_layout "
+                    "ising_import_ref_layout ising_export_bits ising_import_bits ising_dump_lattice "
+                    "ising_run_from_host ising_row_ptr ising_update_color_part ising_accept_count "
+                    "ising_accept_table ising_launch_count ising_kernel_name").split()
+
+
+def accept_count(p, strict=False):
+    return int(load_library().ising_accept_count(C.c_float(float(np.float32(p))), int(bool(strict))))
+
+
+def accept_table(temp):
+    out = (C.c_float * 5)()
+    load_library().ising_accept_table(C.c_float(float(np.float32(temp))), out)
+    return np.array(list(out), dtype=np.float32)
+
+
+def resolve_temperature(temp=None, alpha=None):
+    """-t wins over -a; default alpha 0.1 (optimized/main.cu:1465-1471), all in float32."""
+    if temp is not None and np.float32(temp) != np.float32(-1.0):
+        return np.float32(temp)
+    if alpha is not None and np.float32(alpha) != np.float32(-1.0):
+        return np.float32(alpha) * CRIT_TEMP
+    return ALPHA_DEF * CRIT_TEMP
+
+
+def _ptr(a):
+    return None if a is None else C.c_void_p(a.ctypes.data)
+
+
+class IsingEngine:
+    """One context = `ndev` slabs of Y rows x X columns driven by this process."""
+
+    def __init__(self, X, Y, ndev=1, seed=DEFAULT_SEED, temp=None, alpha=None, xsl=0, ysl=0,
+                 first_device=0, slab_first=0, slab_count=0, flags=0):
+        self._L = load_library()
+        self.X, self.Y, self.ndev, self.seed = int(X), int(Y), int(ndev), int(seed)
+        self.temp = resolve_temperature(temp, alpha)
+        cfg = _Cfg(X=self.X, Y=self.Y, ndev=self.ndev, first_device=int(first_device), seed=self.seed,
+                   temp=float(self.temp), xsl=int(xsl), ysl=int(ysl), slab_first=int(slab_first),
+                   slab_count=int(slab_count), flags=int(flags))
+        h = C.c_void_p()
+        self._h = None
+        self._ck(self._L.ising_create(C.byref(cfg), C.byref(h)))
+        self._h = h
+        self.it = 0                      # sweeps done so far; next sweep uses it+1 (main.cu:1771)
+        self.pitch = self.X // 64        # uint32 words per colour row
+        self.slab_count = int(slab_count) if slab_count else self.ndev
+
+    # -- plumbing --------------------------------------------------------------------------
+    def _ck(self, rc):
+        if rc != 0:
+            raise IsingError(rc, self._L.ising_last_error().decode())
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.ising_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    # -- hot path ----------------------------------------------------------------------------
+    def init_lattice(self):
+        self._ck(self._L.ising_init_lattice(self._h))
+        self.it = 0
+
+    def update_color(self, color, it):
+        self._ck(self._L.ising_update_color(self._h, int(color), int(it)))
+
+    def update_color_part(self, dev, color, it, part, stream=None):
+        self._ck(self._L.ising_update_color_part(self._h, int(dev), int(color), int(it), int(part),
+                                                 C.c_void_p(stream) if stream else None))
+
+    def sweeps(self, n, sync=True):
+        self._ck(self._L.ising_sweeps(self._h, self.it + 1, int(n)))
+        self.it += int(n)
+        if sync:
+            self.sync()
+
+    def sweeps_timed(self, n):
+        ms = C.c_float()
+        self._ck(self._L.ising_sweeps_timed(self._h, self.it + 1, int(n), C.byref(ms)))
+        self.it += int(n)
+        return float(ms.value)
+
+    def sync(self):
+        self._ck(self._L.ising_sync(self._h))
+
+    def set_temperature(self, temp):
+        self.temp = np.float32(temp)
+        self._ck(self._L.ising_set_temperature(self._h, C.c_float(float(self.temp))))
+
+    def set_stream(self, dev, stream):
+        self._ck(self._L.ising_set_stream(self._h, int(dev), C.c_void_p(stream)))
+
+    # -- observables ---------------------------------------------------------------------------
+    def count_spins(self):
+        up, dn = C.c_uint64(), C.c_uint64()
+        self._ck(self._L.ising_count_spins(self._h, C.byref(up), C.byref(dn)))
+        return int(up.value), int(dn.value)
+
+    def magnetization(self):
+        up, dn = self.count_spins()
+        return abs(up - dn) / float(up + dn)      # main.cu:1748
+
+    def bond_sum(self):
+        s = C.c_int64()
+        self._ck(self._L.ising_bond_sum(self._h, C.byref(s)))
+        return int(s.value)
+
+    def energy_per_site(self):
+        return -self.bond_sum() / float(self.ndev * self.Y * self.X)
+
+    # -- transfers -----------------------------------------------------------------------------
+    def export_bits(self, dev=0):
+        b = np.empty((self.Y, self.pitch), dtype=np.uint32)
+        w = np.empty((self.Y, self.pitch), dtype=np.uint32)
+        self._ck(self._L.ising_export_bits(self._h, int(dev), _ptr(b), _ptr(w)))
+        return b, w
+
+    def import_bits(self, black, white, dev=0):
+        b = np.ascontiguousarray(black, dtype=np.uint32)
+        w = np.ascontiguousarray(white, dtype=np.uint32)
+        assert b.shape == (self.Y, self.pitch) and w.shape == (self.Y, self.pitch)
+        self._ck(self._L.ising_import_bits(self._h, int(dev), _ptr(b), _ptr(w)))
+
+    def export_ref_layout(self, dev=0):
+        b = np.empty((self.Y, self.X // 32), dtype=np.uint64)
+        w = np.empty((self.Y, self.X // 32), dtype=np.uint64)
+        self._ck(self._L.ising_export_ref_layout(self._h, int(dev), _ptr(b), _ptr(w)))
+        return b, w
+
+    def import_ref_layout(self, black, white, dev=0):
+        b = np.ascontiguousarray(black, dtype=np.uint64)
+        w = np.ascontiguousarray(white, dtype=np.uint64)
+        self._ck(self._L.ising_import_ref_layout(self._h, int(dev), _ptr(b), _ptr(w)))
+
+    def dump_lattice(self, prefix):
+        self._ck(self._L.ising_dump_lattice(self._h, os.fsencode(prefix)))
+
+    def run_from_host(self, black_in, white_in, n, black_out, white_out, counts=True):
+        up, dn = C.c_uint64(), C.c_uint64()
+        self._ck(self._L.ising_run_from_host(self._h, _ptr(black_in), _ptr(white_in), self.it + 1, int(n),
+                                             _ptr(black_out), _ptr(white_out),
+                                             C.byref(up) if counts else None, C.byref(dn) if counts else None))
+        self.it += int(n)
+        return int(up.value), int(dn.value)
+
+    def row_ptr(self, dev, color, row):
+        p, n = C.c_void_p(), C.c_size_t()
+        self._ck(self._L.ising_row_ptr(self._h, int(dev), int(color), int(row), C.byref(p), C.byref(n)))
+        return int(p.value), int(n.value)
+
+    @property
+    def launches(self):
+        return int(self._L.ising_launch_count(self._h))
+
+    @property
+    def kernel_name(self):
+        return self._L.ising_kernel_name(self._h).decode()
