@@ -154,6 +154,12 @@ uint64_t ising_accept_count(float p, int strict);
 /* The 5 acceptance probabilities by number of ALIGNED neighbours a = 0..4 for temperature
  * temp, i.e. exp_h[1][a] of main.cu:1683-1697 (host expf). */
 void ising_accept_table(float temp, float out[5]);
+/* The four raw Philox outputs that decide sites 32*word + {2q, 16+2q, 2q+1, 17+2q} of colour
+ * `color` in global row `grow` at iteration `it` (0 = lattice init) for an X-column lattice,
+ * computed on the host through the same folded schedule the kernels use (philox_map.h).
+ * Lets tests check the site -> (subsequence, counter, lane) contract without a GPU. */
+void ising_site_random(uint64_t seed, int32_t X, int it, int color, uint32_t grow, uint32_t word, int q,
+                       uint32_t out[4]);
 /* kernels launched by this context since creation (bench.py's gpu_launches). */
 uint64_t ising_launch_count(const ising_ctx* ctx);
 /* name of the update kernel variant in use, for logs */

@@ -7,7 +7,7 @@ There is no CPU fallback: every compute call goes to the CUDA library and raises
 is missing or no sm_100 GPU is visible.
 """
 from .engine import (CRIT_TEMP, DEFAULT_SEED, IsingEngine, IsingError, accept_count,  # noqa: F401
-                     accept_table, lib_path, load_library, resolve_temperature)
+                     accept_table, lib_path, load_library, resolve_temperature, site_random)
 
 __all__ = ["IsingEngine", "IsingError", "load_library", "lib_path", "accept_count", "accept_table",
-           "resolve_temperature", "DEFAULT_SEED", "CRIT_TEMP"]
+           "resolve_temperature", "site_random", "DEFAULT_SEED", "CRIT_TEMP"]

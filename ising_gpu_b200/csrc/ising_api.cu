@@ -194,6 +194,16 @@ void ising_accept_table(float temp, float out[5]) { accept_table(temp, out); }
 uint64_t ising_launch_count(const ising_ctx* ctx) { return ctx ? ctx->launches : 0; }
 const char* ising_kernel_name(const ising_ctx* ctx) { return update_kernel_name(ctx ? ctx->rule.fast : 1); }
 
+void ising_site_random(uint64_t seed, int32_t X, int it, int color, uint32_t grow, uint32_t word, int q,
+                       uint32_t out[4])
+{
+    const StepTables st = make_step_tables(seed, 2ull * (uint64_t)it + (uint64_t)color);
+    const uint32_t tid = ref_tid(grow, word, (uint32_t)(X / 2048));
+    const ThreadConsts tc = make_thread_consts(tid, st.x1, st.k1r3);
+    const int cl = 8 * (int)((word % 32u) / 16u) + q;
+    philox_fast(tc, st.a[cl], st.b[cl], st.d[cl], st.k0, st.k1, out);
+}
+
 int ising_create(const ising_cfg* cfg, ising_ctx** out)
 {
     if (!cfg || !out) return fail(ISING_EINVAL, "null argument");

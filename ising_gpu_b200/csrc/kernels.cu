@@ -60,26 +60,28 @@ __device__ __forceinline__ void tma_store_commit_wait()
 }
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-// acc = 2*acc + (x > thr): the compare lands in the carry flag and is shifted in by the
-// add-with-carry (IADD3 + IADD3.X / IMAD.X in SASS).  Rejected sites accumulate as 1 bits.
-__device__ __forceinline__ void shift_in_reject(uint32_t& acc, uint32_t x, uint32_t thr)
+// acc = 2*acc + (x > thr): x + ~thr carries out of 32 bits exactly when x > thr; the carry
+// flag is shifted in by the add-with-carry (IADD3 + IADD3.X / IMAD.X in SASS).  Rejected
+// sites accumulate as 1 bits.  nthr = ~thr.
+__device__ __forceinline__ void shift_in_reject(uint32_t& acc, uint32_t x, uint32_t nthr)
 {
     asm("{\n"
         ".reg .u32 t;\n"
-        "sub.cc.u32 t, %2, %1;\n"
+        "add.cc.u32 t, %1, %2;\n"
         "addc.u32 %0, %0, %0;\n"
         "}\n"
         : "+r"(acc)
-        : "r"(x), "r"(thr));
+        : "r"(x), "r"(nthr));
 }
 
 // Reject masks of one 32-site word: 8 Philox calls, outputs x,y,z,w -> bits 2q, 16+2q, 2q+1,
 // 17+2q.  Calls run q = 7..0 so that shifting in z then x (w then y) leaves bit k of the
 // 16-bit accumulators == site k.
 template <int NTHR, int J>
-__device__ __forceinline__ void word_reject_masks(const ThreadConsts& tc, const StepTables& st, uint32_t thrA,
-                                                  uint32_t thrB, uint32_t& rejA, uint32_t& rejB)
+__device__ __forceinline__ void word_reject_masks(const ThreadConsts& tc, const StepTables& st, uint32_t thrA_,
+                                                  uint32_t thrB_, uint32_t& rejA, uint32_t& rejB)
 {
+    const uint32_t thrA = ~thrA_, thrB = ~thrB_;
     uint32_t a_lo = 0, a_hi = 0, b_lo = 0, b_hi = 0;
 #pragma unroll
     for (int q = 7; q >= 0; q--) {

@@ -72,6 +72,7 @@ def load_library():
         "ising_update_color_part": ([vp, C.c_int, C.c_int, C.c_int, C.c_int, vp], C.c_int),
         "ising_accept_count": ([C.c_float, C.c_int], C.c_uint64),
         "ising_accept_table": ([C.c_float, C.POINTER(C.c_float)], None),
+        "ising_site_random": ([C.c_uint64, C.c_int32, C.c_int, C.c_int, C.c_uint32, C.c_uint32, C.c_int, u32p], None),
         "ising_launch_count": ([vp], C.c_uint64),
         "ising_kernel_name": ([vp], C.c_char_p),
     }
@@ -87,7 +88,7 @@ EXPORTED_SYMBOLS = ("ising_create ising_destroy ising_last_error ising_abi_versi
                     "ising_set_temperature ising_count_spins ising_bond_sum ising_export_ref_layout "
                     "ising_import_ref_layout ising_export_bits ising_import_bits ising_dump_lattice "
                     "ising_run_from_host ising_row_ptr ising_update_color_part ising_accept_count "
-                    "ising_accept_table ising_launch_count ising_kernel_name").split()
+                    "ising_accept_table ising_site_random ising_launch_count ising_kernel_name").split()
 
 
 def accept_count(p, strict=False):
@@ -98,6 +99,12 @@ def accept_table(temp):
     out = (C.c_float * 5)()
     load_library().ising_accept_table(C.c_float(float(np.float32(temp))), out)
     return np.array(list(out), dtype=np.float32)
+
+
+def site_random(seed, X, it, color, grow, word, q):
+    out = (C.c_uint32 * 4)()
+    load_library().ising_site_random(int(seed), int(X), int(it), int(color), int(grow), int(word), int(q), out)
+    return tuple(int(v) for v in out)
 
 
 def resolve_temperature(temp=None, alpha=None):
