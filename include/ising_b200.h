@@ -146,6 +146,14 @@ int ising_row_ptr(ising_ctx* ctx, int dev, int color, int row, void** dptr, size
 enum { ISING_PART_ALL = 0, ISING_PART_EDGES = 1, ISING_PART_INTERIOR = 2 };
 int ising_update_color_part(ising_ctx* ctx, int dev, int color, int it, int part, void* stream);
 
+/* ---- device queries used by the CLI banner (main.cu:1483-1536) ---------------------------*/
+int ising_device_count(int* count);
+/* name (up to name_len bytes), #SMs, max threads per SM, compute capability, ECC flag */
+int ising_device_info(int device, char* name, size_t name_len, int* sms, int* max_threads_per_sm,
+                      int* cc_major, int* cc_minor, int* ecc);
+/* *ok = 1 when `device` can map `peer`'s memory (cudaDeviceCanAccessPeer) */
+int ising_can_access_peer(int device, int peer, int* ok);
+
 /* ---- introspection used by tests and bench ----------------------------------------------*/
 /* Number of 32-bit Philox outputs x accepted by `uniform(x) <= p` (strict = 0) or
  * `uniform(x) < p` (strict = 1), uniform(x) = x*2^-32 + 2^-33 in float (curand_uniform).

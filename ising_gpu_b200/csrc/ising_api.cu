@@ -129,6 +129,7 @@ UpdateParams base_params(const ising_ctx* c, int dev, int color, int it)
     p.grid_x = (uint32_t)(c->cfg.X / 2048);
     p.grow0 = (uint32_t)(c->cfg.slab_first + dev) * (uint32_t)c->cfg.Y;
     p.rows = c->cfg.Y;
+    p.pitch = c->pitch;
     p.yperiod = c->yperiod;
     p.xperiod = c->xperiod;
     p.color = color;
@@ -150,7 +151,7 @@ int launch_part(ising_ctx* c, int dev, int color, int it, int part, cudaStream_t
         if (gy <= 0) return ISING_OK;
     }
     CU_TRY(cudaSetDevice(d.device));
-    launch_update(d.map_tile[src], d.map_row[src], d.map_side[src], d.map_tile[color], p, tiles_x, gy, stream);
+    launch_update(d.map_tile[src], d.map_row[src], d.map_side[src], local_row(c, d, color, 0), p, tiles_x, gy, stream);
     CU_TRY(cudaGetLastError());
     c->launches++;
     return ISING_OK;
@@ -193,6 +194,34 @@ uint64_t ising_accept_count(float p, int strict) { return accept_count(p, strict
 void ising_accept_table(float temp, float out[5]) { accept_table(temp, out); }
 uint64_t ising_launch_count(const ising_ctx* ctx) { return ctx ? ctx->launches : 0; }
 const char* ising_kernel_name(const ising_ctx* ctx) { return update_kernel_name(ctx ? ctx->rule.fast : 1); }
+
+int ising_device_count(int* count)
+{
+    if (!count) return fail(ISING_EINVAL, "null argument");
+    CU_TRY(cudaGetDeviceCount(count));
+    return ISING_OK;
+}
+
+int ising_device_info(int device, char* name, size_t name_len, int* sms, int* max_threads_per_sm, int* cc_major,
+                      int* cc_minor, int* ecc)
+{
+    cudaDeviceProp p;
+    CU_TRY(cudaGetDeviceProperties(&p, device));
+    if (name && name_len) { strncpy(name, p.name, name_len - 1); name[name_len - 1] = 0; }
+    if (sms) *sms = p.multiProcessorCount;
+    if (max_threads_per_sm) *max_threads_per_sm = p.maxThreadsPerMultiProcessor;
+    if (cc_major) *cc_major = p.major;
+    if (cc_minor) *cc_minor = p.minor;
+    if (ecc) *ecc = p.ECCEnabled;
+    return ISING_OK;
+}
+
+int ising_can_access_peer(int device, int peer, int* ok)
+{
+    if (!ok) return fail(ISING_EINVAL, "null argument");
+    CU_TRY(cudaDeviceCanAccessPeer(ok, device, peer));
+    return ISING_OK;
+}
 
 void ising_site_random(uint64_t seed, int32_t X, int it, int color, uint32_t grow, uint32_t word, int q,
                        uint32_t out[4])

@@ -74,33 +74,154 @@ __device__ __forceinline__ void shift_in_reject(uint32_t& acc, uint32_t x, uint3
         : "r"(x), "r"(nthr));
 }
 
-// Reject masks of one 32-site word: 8 Philox calls, outputs x,y,z,w -> bits 2q, 16+2q, 2q+1,
-// 17+2q.  Calls run q = 7..0 so that shifting in z then x (w then y) leaves bit k of the
-// 16-bit accumulators == site k.
-template <int NTHR, int J>
-__device__ __forceinline__ void word_reject_masks(const ThreadConsts& tc, const StepTables& st, uint32_t thrA_,
-                                                  uint32_t thrB_, uint32_t& rejA, uint32_t& rejB)
+// acc |= (x > thr) << BIT as one compare and one predicated OR-immediate.
+__device__ __forceinline__ void or_bit_if_gt(uint32_t& acc, uint32_t x, uint32_t thr, int bit)
 {
-    const uint32_t thrA = ~thrA_, thrB = ~thrB_;
+    asm("{\n"
+        ".reg .pred p;\n"
+        "setp.gt.u32 p, %1, %2;\n"
+        "@p or.b32 %0, %0, %3;\n"
+        "}\n"
+        : "+r"(acc)
+        : "r"(x), "r"(thr), "r"(1u << bit));   // bit is a literal after unrolling
+}
+
+// acc += 2^bit if x > thr, in FP32 (exact: acc < 2^24).
+__device__ __forceinline__ void fadd_bit_if_gt(float& acc, uint32_t x, uint32_t thr, int bit)
+{
+    asm("{\n"
+        ".reg .pred p;\n"
+        "setp.gt.u32 p, %1, %2;\n"
+        "@p add.f32 %0, %0, %3;\n"
+        "}\n"
+        : "+f"(acc)
+        : "r"(x), "r"(thr), "f"((float)(1u << bit)));
+}
+
+// Reject masks of one 32-site word: 8 Philox calls, outputs x,y,z,w -> bits 2q, 16+2q, 2q+1,
+// 17+2q.
+#ifndef ISING_ACC_VARIANT
+#define ISING_ACC_VARIANT 1
+#endif
+#ifndef ISING_CARRY_CALLS
+#define ISING_CARRY_CALLS 2
+#endif
+template <int NTHR, int J>
+__device__ __forceinline__ void word_reject_masks(const ThreadConsts& tc, const StepTables& st, uint32_t thrA,
+                                                  uint32_t thrB, uint32_t zero, uint32_t& rejA, uint32_t& rejB)
+{
+#if ISING_ACC_VARIANT == 0
+    // carry chain: calls run q = 7..0 so that shifting in z then x (w then y) leaves bit k of
+    // the 16-bit accumulators == site k
+    const uint32_t nA = ~thrA, nB = ~thrB;
     uint32_t a_lo = 0, a_hi = 0, b_lo = 0, b_hi = 0;
 #pragma unroll
     for (int q = 7; q >= 0; q--) {
         const int cl = 8 * J + q;
         uint32_t o[4];
         philox_fast(tc, st.a[cl], st.b[cl], st.d[cl], st.k0, st.k1, o);
-        shift_in_reject(a_lo, o[2], thrA);
-        shift_in_reject(a_lo, o[0], thrA);
-        shift_in_reject(a_hi, o[3], thrA);
-        shift_in_reject(a_hi, o[1], thrA);
+        shift_in_reject(a_lo, o[2], nA);
+        shift_in_reject(a_lo, o[0], nA);
+        shift_in_reject(a_hi, o[3], nA);
+        shift_in_reject(a_hi, o[1], nA);
         if (NTHR > 1) {
-            shift_in_reject(b_lo, o[2], thrB);
-            shift_in_reject(b_lo, o[0], thrB);
-            shift_in_reject(b_hi, o[3], thrB);
-            shift_in_reject(b_hi, o[1], thrB);
+            shift_in_reject(b_lo, o[2], nB);
+            shift_in_reject(b_lo, o[0], nB);
+            shift_in_reject(b_hi, o[3], nB);
+            shift_in_reject(b_hi, o[1], nB);
         }
     }
     rejA = __byte_perm(a_lo, a_hi, 0x5410);
     rejB = (NTHR > 1) ? __byte_perm(b_lo, b_hi, 0x5410) : 0u;
+#elif ISING_ACC_VARIANT == 1
+    // compare + predicated OR of the site's bit: ISETP + @P LOP3, both on the ALU pipe
+    uint32_t a = 0, b = 0;
+#pragma unroll
+    for (int q = 0; q < 8; q++) {
+        const int cl = 8 * J + q;
+        uint32_t o[4];
+        philox_fast(tc, st.a[cl], st.b[cl], st.d[cl], st.k0, st.k1, o);
+        or_bit_if_gt(a, o[0], thrA, 2 * q);
+        or_bit_if_gt(a, o[1], thrA, 16 + 2 * q);
+        or_bit_if_gt(a, o[2], thrA, 2 * q + 1);
+        or_bit_if_gt(a, o[3], thrA, 17 + 2 * q);
+        if (NTHR > 1) {
+            or_bit_if_gt(b, o[0], thrB, 2 * q);
+            or_bit_if_gt(b, o[1], thrB, 16 + 2 * q);
+            or_bit_if_gt(b, o[2], thrB, 2 * q + 1);
+            or_bit_if_gt(b, o[3], thrB, 17 + 2 * q);
+        }
+    }
+    rejA = a;
+    rejB = b;
+#elif ISING_ACC_VARIANT == 2
+    // FP32 accumulators (predicated FADD of 2^k): measured no faster -- FMA-lite shares its
+    // dispatch with FMA-heavy, so the FADDs still compete with the IMAD.WIDEs.
+    float a_lo = 8388608.0f, a_hi = 8388608.0f, b_lo = 8388608.0f, b_hi = 8388608.0f;
+#pragma unroll
+    for (int q = 0; q < 8; q++) {
+        const int cl = 8 * J + q;
+        uint32_t o[4];
+        philox_fast(tc, st.a[cl], st.b[cl], st.d[cl], st.k0, st.k1, o);
+        fadd_bit_if_gt(a_lo, o[0], thrA, 2 * q);
+        fadd_bit_if_gt(a_hi, o[1], thrA, 2 * q);
+        fadd_bit_if_gt(a_lo, o[2], thrA, 2 * q + 1);
+        fadd_bit_if_gt(a_hi, o[3], thrA, 2 * q + 1);
+        if (NTHR > 1) {
+            fadd_bit_if_gt(b_lo, o[0], thrB, 2 * q);
+            fadd_bit_if_gt(b_hi, o[1], thrB, 2 * q);
+            fadd_bit_if_gt(b_lo, o[2], thrB, 2 * q + 1);
+            fadd_bit_if_gt(b_hi, o[3], thrB, 2 * q + 1);
+        }
+    }
+    rejA = __byte_perm(__float_as_uint(a_lo), __float_as_uint(a_hi), 0x5410);
+    rejB = (NTHR > 1) ? __byte_perm(__float_as_uint(b_lo), __float_as_uint(b_hi), 0x5410) : 0u;
+#else
+    // Pipe-balanced form (pipe map measured on B200 with tools/pipe_map.cu): the FMA pipe is
+    // held 4 cycles by every IMAD.WIDE and is the binding resource; the ALU pipe carries the
+    // Philox XORs and the compares.  The masks of the top ISING_CARRY_CALLS calls are built
+    // with the carry chain (compare on ALU, shift-in as IMAD.X on FMA), the rest with compare +
+    // predicated OR (both ALU), which levels the two pipes.
+    constexpr int NC = ISING_CARRY_CALLS;
+    const uint32_t nA = ~thrA, nB = ~thrB;
+    uint32_t a = zero, b = zero;                        // `zero` is a run-time 0: keeps the ORs LOP3
+    uint32_t ca_lo = 0, ca_hi = 0, cb_lo = 0, cb_hi = 0;  // carry-chain accumulators, sites 16-2NC..15
+#pragma unroll
+    for (int q = 7; q >= 0; q--) {
+        const int cl = 8 * J + q;
+        uint32_t o[4];
+        philox_fast(tc, st.a[cl], st.b[cl], st.d[cl], st.k0, st.k1, o);
+        if (q >= 8 - NC) {
+            shift_in_reject(ca_lo, o[2], nA);
+            shift_in_reject(ca_lo, o[0], nA);
+            shift_in_reject(ca_hi, o[3], nA);
+            shift_in_reject(ca_hi, o[1], nA);
+            if (NTHR > 1) {
+                shift_in_reject(cb_lo, o[2], nB);
+                shift_in_reject(cb_lo, o[0], nB);
+                shift_in_reject(cb_hi, o[3], nB);
+                shift_in_reject(cb_hi, o[1], nB);
+            }
+        } else {
+            or_bit_if_gt(a, o[0], thrA, 2 * q);
+            or_bit_if_gt(a, o[1], thrA, 16 + 2 * q);
+            or_bit_if_gt(a, o[2], thrA, 2 * q + 1);
+            or_bit_if_gt(a, o[3], thrA, 17 + 2 * q);
+            if (NTHR > 1) {
+                or_bit_if_gt(b, o[0], thrB, 2 * q);
+                or_bit_if_gt(b, o[1], thrB, 16 + 2 * q);
+                or_bit_if_gt(b, o[2], thrB, 2 * q + 1);
+                or_bit_if_gt(b, o[3], thrB, 17 + 2 * q);
+            }
+        }
+    }
+    if (NC > 0) {   // the chain masks cover sites 16-2NC..15 of each half
+        a |= (ca_lo << ((16 - 2 * NC) & 31)) | (ca_hi << ((32 - 2 * NC) & 31));
+        b |= (cb_lo << ((16 - 2 * NC) & 31)) | (cb_hi << ((32 - 2 * NC) & 31));
+    }
+    rejA = a;
+    rejB = b;
+#endif
 }
 
 // Flip mask of one word from its own spins, the four neighbour words and the reject masks.
@@ -130,25 +251,36 @@ __device__ __forceinline__ uint32_t flip_mask(uint32_t me, uint32_t up, uint32_t
 
 // ------------------------------------------------------------------------------------------
 // Colour half-sweep.  One CTA = one 16 x 32-word tile, one thread = one reference thread id
-// (words tx and tx+16 of row ty).  Six TMA boxes per tile: source centre, source row above,
-// source row below, 16-byte source boxes left and right, and the tile's own spins; one TMA
-// store writes the tile back.
+// (words tx and tx+16 of row ty).  Five TMA boxes stage the source colour: centre, the row
+// above, the row below and a 16-byte box left and right; their coordinates carry the periodic
+// wrap.  The tile's own words are private to their thread: loaded straight into registers at
+// kernel entry and stored straight back, so that warps never meet at a CTA barrier after the
+// prologue (a closing __syncthreads for a TMA store cost 27 % of warp time in barrier stalls).
 // ------------------------------------------------------------------------------------------
+#ifndef ISING_MIN_BLOCKS
+#define ISING_MIN_BLOCKS 4
+#endif
 template <bool FAST>
-__global__ void __launch_bounds__(UPDATE_THREADS, 4)
+__global__ void __launch_bounds__(UPDATE_THREADS, ISING_MIN_BLOCKS)
 update_color_kernel(const __grid_constant__ CUtensorMap src_tile, const __grid_constant__ CUtensorMap src_row,
-                    const __grid_constant__ CUtensorMap src_side, const __grid_constant__ CUtensorMap dst_tile,
+                    const __grid_constant__ CUtensorMap src_side, uint32_t* __restrict__ dst /* local row 0 */,
                     const __grid_constant__ UpdateParams p)
 {
     __shared__ alignas(128) uint32_t sV[(TH + 2) * TW];   // rows: above, 16 centre rows, below
     __shared__ alignas(128) uint32_t sL[TH * SIDE_W];
     __shared__ alignas(128) uint32_t sR[TH * SIDE_W];
-    __shared__ alignas(128) uint32_t sD[TH * TW];         // own colour, updated in place
     __shared__ alignas(8) uint64_t bar;
 
     const int tile_row = p.edges_mode ? (blockIdx.y == 0 ? p.tile_row0 : p.tile_row_alt) : p.tile_row0 + (int)blockIdx.y;
     const int x0 = blockIdx.x * TW;       // first word of the tile in the row
     const int y0 = tile_row * TH;         // first local row of the tile
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+
+    // own spins: two 32-site words per thread, in flight while the random numbers are made
+    uint32_t* const my = dst + (size_t)(y0 + ty) * p.pitch + x0 + tx;
+    uint32_t me[2];
+    me[0] = my[0];
+    me[1] = my[16];
 
     if (threadIdx.x == 0) {
         mbar_init(&bar, 1);
@@ -166,7 +298,7 @@ update_color_kernel(const __grid_constant__ CUtensorMap src_tile, const __grid_c
         }
         const int xl = (x0 % p.xperiod == 0) ? x0 + p.xperiod - 1 : x0 - 1;
         const int xr = ((x0 + TW) % p.xperiod == 0) ? x0 + TW - p.xperiod : x0 + TW;
-        constexpr uint32_t bytes = ((TH + 2) * TW + 2 * TH * SIDE_W + TH * TW) * 4;
+        constexpr uint32_t bytes = ((TH + 2) * TW + 2 * TH * SIDE_W) * 4;
         mbar_expect_tx(&bar, bytes);
         // allocation row = local row + 1 (row 0 of the allocation is the upper ghost row)
         tma_load_2d(sV + TW, &src_tile, x0, y0 + 1, &bar);
@@ -174,10 +306,8 @@ update_color_kernel(const __grid_constant__ CUtensorMap src_tile, const __grid_c
         tma_load_2d(sV + (TH + 1) * TW, &src_row, x0, ybot + 1, &bar);
         tma_load_2d(sL, &src_side, xl - (SIDE_W - 1), y0 + 1, &bar);
         tma_load_2d(sR, &src_side, xr, y0 + 1, &bar);
-        tma_load_2d(sD, &dst_tile, x0, y0 + 1, &bar);
     }
 
-    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
     const uint32_t grow = p.grow0 + (uint32_t)(y0 + ty);
     const uint32_t tid = ref_tid(grow, (uint32_t)(x0 + tx), p.grid_x);
     const ThreadConsts tc = make_thread_consts(tid, p.st.x1, p.st.k1r3);
@@ -186,11 +316,11 @@ update_color_kernel(const __grid_constant__ CUtensorMap src_tile, const __grid_c
 
     uint32_t rejA[2], rejB[2];
     if (FAST || p.rule.selB[0] | p.rule.selB[1] | p.rule.selB[2] | p.rule.selB[3] | p.rule.selB[4]) {
-        word_reject_masks<2, 0>(tc, p.st, p.rule.thrA, p.rule.thrB, rejA[0], rejB[0]);
-        word_reject_masks<2, 1>(tc, p.st, p.rule.thrA, p.rule.thrB, rejA[1], rejB[1]);
+        word_reject_masks<2, 0>(tc, p.st, p.rule.thrA, p.rule.thrB, p.zero, rejA[0], rejB[0]);
+        word_reject_masks<2, 1>(tc, p.st, p.rule.thrA, p.rule.thrB, p.zero, rejA[1], rejB[1]);
     } else {
-        word_reject_masks<1, 0>(tc, p.st, p.rule.thrA, p.rule.thrB, rejA[0], rejB[0]);
-        word_reject_masks<1, 1>(tc, p.st, p.rule.thrA, p.rule.thrB, rejA[1], rejB[1]);
+        word_reject_masks<1, 0>(tc, p.st, p.rule.thrA, p.rule.thrB, p.zero, rejA[0], rejB[0]);
+        word_reject_masks<1, 1>(tc, p.st, p.rule.thrA, p.rule.thrB, p.zero, rejA[1], rejB[1]);
     }
 
     mbar_wait(&bar, 0);
@@ -201,7 +331,6 @@ update_color_kernel(const __grid_constant__ CUtensorMap src_tile, const __grid_c
         const uint32_t up = sV[ty * TW + w];
         const uint32_t ct = sV[(ty + 1) * TW + w];
         const uint32_t dn = sV[(ty + 2) * TW + w];
-        const uint32_t me = sD[ty * TW + w];
         uint32_t sd;
         if (read_back) {
             const uint32_t prev = (w == 0) ? sL[ty * SIDE_W + SIDE_W - 1] : sV[(ty + 1) * TW + w - 1];
@@ -210,25 +339,18 @@ update_color_kernel(const __grid_constant__ CUtensorMap src_tile, const __grid_c
             const uint32_t next = (w == TW - 1) ? sR[ty * SIDE_W] : sV[(ty + 1) * TW + w + 1];
             sd = __funnelshift_r(ct, next, 1);    // (ct >> 1) | (next << 31)
         }
-        sD[ty * TW + w] = me ^ flip_mask<FAST>(me, up, dn, ct, sd, rejA[j], rejB[j], p.rule);
-    }
-
-    fence_proxy_async_smem();     // generic-proxy writes to sD -> visible to the TMA store
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        tma_store_2d(&dst_tile, x0, y0 + 1, sD);
-        tma_store_commit_wait();
+        my[16 * j] = me[j] ^ flip_mask<FAST>(me[j], up, dn, ct, sd, rejA[j], rejB[j], p.rule);
     }
 }
 
 void launch_update(const CUtensorMap& src_tile, const CUtensorMap& src_row, const CUtensorMap& src_side,
-                   const CUtensorMap& dst_tile, const UpdateParams& p, int tiles_x, int tiles_y, cudaStream_t stream)
+                   uint32_t* dst, const UpdateParams& p, int tiles_x, int tiles_y, cudaStream_t stream)
 {
     const dim3 grid((unsigned)tiles_x, (unsigned)tiles_y);
     if (p.rule.fast)
-        update_color_kernel<true><<<grid, UPDATE_THREADS, 0, stream>>>(src_tile, src_row, src_side, dst_tile, p);
+        update_color_kernel<true><<<grid, UPDATE_THREADS, 0, stream>>>(src_tile, src_row, src_side, dst, p);
     else
-        update_color_kernel<false><<<grid, UPDATE_THREADS, 0, stream>>>(src_tile, src_row, src_side, dst_tile, p);
+        update_color_kernel<false><<<grid, UPDATE_THREADS, 0, stream>>>(src_tile, src_row, src_side, dst, p);
 }
 
 const char* update_kernel_name(int fast)
@@ -250,8 +372,8 @@ __global__ void __launch_bounds__(UPDATE_THREADS) init_kernel(uint32_t* __restri
     const uint32_t tid = ref_tid(grow, (uint32_t)(x0 + tx), p.grid_x);
     const ThreadConsts tc = make_thread_consts(tid, p.st.x1, p.st.k1r3);
     uint32_t rej0, rej1, unused;
-    word_reject_masks<1, 0>(tc, p.st, p.thr_half, 0u, rej0, unused);
-    word_reject_masks<1, 1>(tc, p.st, p.thr_half, 0u, rej1, unused);
+    word_reject_masks<1, 0>(tc, p.st, p.thr_half, 0u, p.zero, rej0, unused);
+    word_reject_masks<1, 1>(tc, p.st, p.thr_half, 0u, p.zero, rej1, unused);
     uint32_t* r = plane + (size_t)row * p.pitch + x0 + tx;
     r[0] = ~rej0;
     r[16] = ~rej1;

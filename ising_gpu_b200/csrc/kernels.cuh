@@ -34,9 +34,11 @@ struct UpdateParams {
     int tile_row_alt;       // edges mode: tile row handled by blockIdx.y == 1
     int edges_mode;
     int rows;               // local rows Y
+    int pitch;              // words per row
     int yperiod;            // vertical wrap period in rows inside the slab; 0 = ghost rows
     int xperiod;            // horizontal wrap period in words
     int color;
+    uint32_t zero;          // always 0; a value ptxas cannot see through (see word_reject_masks)
 };
 
 struct InitParams {
@@ -46,11 +48,11 @@ struct InitParams {
     uint32_t grow0;
     int rows;
     int pitch;              // words per row
+    uint32_t zero;
 };
 
 void launch_update(const CUtensorMap& src_tile, const CUtensorMap& src_row, const CUtensorMap& src_side,
-                   const CUtensorMap& dst_tile, const UpdateParams& p, int tiles_x, int tiles_y,
-                   cudaStream_t stream);
+                   uint32_t* dst_local_row0, const UpdateParams& p, int tiles_x, int tiles_y, cudaStream_t stream);
 void launch_init(uint32_t* plane, const InitParams& p, cudaStream_t stream);
 // counts[0] += popcount over rows 0..rows-1 of the plane
 void launch_count(const uint32_t* plane, int rows, int pitch, unsigned long long* counts, cudaStream_t stream);

@@ -35,7 +35,8 @@ class _Cfg(C.Structure):
 
 
 def lib_path():
-    return os.path.join(_HERE, "libising_b200.so")
+    # ISING_B200_LIB: developer override to A/B kernel variants; the product is the in-tree build
+    return os.environ.get("ISING_B200_LIB") or os.path.join(_HERE, "libising_b200.so")
 
 
 def load_library():
@@ -70,6 +71,9 @@ def load_library():
         "ising_run_from_host": ([vp, vp, vp, C.c_int, C.c_int, vp, vp, u64p, u64p], C.c_int),
         "ising_row_ptr": ([vp, C.c_int, C.c_int, C.c_int, C.POINTER(vp), C.POINTER(C.c_size_t)], C.c_int),
         "ising_update_color_part": ([vp, C.c_int, C.c_int, C.c_int, C.c_int, vp], C.c_int),
+        "ising_device_count": ([C.POINTER(C.c_int)], C.c_int),
+        "ising_device_info": ([C.c_int, C.c_char_p, C.c_size_t] + [C.POINTER(C.c_int)] * 5, C.c_int),
+        "ising_can_access_peer": ([C.c_int, C.c_int, C.POINTER(C.c_int)], C.c_int),
         "ising_accept_count": ([C.c_float, C.c_int], C.c_uint64),
         "ising_accept_table": ([C.c_float, C.POINTER(C.c_float)], None),
         "ising_site_random": ([C.c_uint64, C.c_int32, C.c_int, C.c_int, C.c_uint32, C.c_uint32, C.c_int, u32p], None),
@@ -88,6 +92,7 @@ EXPORTED_SYMBOLS = ("ising_create ising_destroy ising_last_error ising_abi_versi
                     "ising_set_temperature ising_count_spins ising_bond_sum ising_export_ref_layout "
                     "ising_import_ref_layout ising_export_bits ising_import_bits ising_dump_lattice "
                     "ising_run_from_host ising_row_ptr ising_update_color_part ising_accept_count "
+                    "ising_device_count ising_device_info ising_can_access_peer "
                     "ising_accept_table ising_site_random ising_launch_count ising_kernel_name").split()
 
 
