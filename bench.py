@@ -1,0 +1,351 @@
+#!/usr/bin/env python
+"""bench.py -- spin-flip attempts/ns of the checkerboard Metropolis hot path on N B200s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
+
+Workload (BASELINE.json): 65536 x 65536 lattice per GPU at T = 1.5, default seed; at N GPUs the
+lattice is N slabs stacked along Y (131072 x 65536 at 2, 262144 x 65536 at 4 and -- as the
+north star names it -- 262144 x 65536 at 8, i.e. 32768 rows per GPU there; --rows-per-gpu
+overrides).  A "step" is --sweeps-per-step (16) full sweeps (black + white colour update with
+its halo exchange).  The timed region holds exactly K steps, bracketed by a barrier and a
+device synchronize, timed with CUDA events on the launching stream, max over ranks.
+
+One JSON line on rank 0.  `value` = total flip attempts of all ranks / that time, lattice
+resident in HBM.  `e2e` = same metric through the C ABI with HOST buffers: every step uploads
+both colour planes from pinned memory, sweeps, downloads the planes and the spin counts.
+`roofline` = algorithmic bytes (0.25 B per flip attempt) over the measured kernel
+time against the measured HBM peak; `cpu_baseline` = numpy restatement of basic_python timed
+on this box's host (1 core), plus the C/OpenMP oracle on all cores as `cpu_oracle`.
+
+--impl reference: runs the UNMODIFIED reference (optimized/main.cu rebuilt for sm_100a as
+oracle/_ref/cuIsing_ref) through its own CLI on the same lattice; under torchrun only rank 0
+runs it (cuIsing_ref -d N drives all N GPUs from one process, as the reference does).  If the
+binary is absent it times the CPU oracle port on all host cores instead and says so.
+"""
+import argparse
+import json
+import os
+import re
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+X_COLS = 65536
+TEMP = 1.5
+ALG_BYTES_PER_FLIP = 0.25      # each spin read once + written once per sweep at 1 bit/spin
+REF_BYTES_PER_FLIP = 1.5       # the reference's own accounting, optimized/main.cu:1887-1890
+
+
+def default_rows(n):
+    return 32768 if n >= 8 else 65536
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled during the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.lines, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(device), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return None
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1])); pw.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return None
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "power_w_max": max(pw), "samples": len(sm),
+                "reasons": sorted(reasons)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic_per_launch():
+    """dram bytes per update launch from the committed ncu capture, or None."""
+    p = os.path.join(ROOT, "profiles", "update_kernel_ncu_summary.json")
+    try:
+        d = json.load(open(p))
+        return float(d["dram_bytes_read"]) + float(d["dram_bytes_write"])
+    except Exception:
+        return None
+
+
+def cpu_baselines():
+    from oracle import ising_oracle, numpy_basic
+    n = 4096
+    sweeps = 24
+    fl, mag, secs = numpy_basic.run(n=n, m=n, alpha=TEMP / numpy_basic.TCRIT, sweeps=sweeps, seed=1234)
+    base = {"value": round(fl, 5), "unit": "flips/ns", "cores": 1, "host_cores": os.cpu_count(), "kind": "port",
+            "sample": "numpy restatement of basic_python/ising_basic.py update_lattice, %dx%d, T=%.1f, %d sweeps, "
+                      "%.1f s" % (n, n, TEMP, sweeps, secs)}
+    L = ising_oracle.OracleLattice(X_COLS, 4096)
+    L.init()
+    t0 = time.perf_counter()
+    L.sweeps(2, TEMP)
+    dt = time.perf_counter() - t0
+    L.close()
+    orc = {"value": round(X_COLS * 4096 * 2 / dt * 1e-9, 4), "unit": "flips/ns", "cores": ising_oracle.num_threads(),
+           "kind": "port", "sample": "bit-exact C/OpenMP oracle of optimized/, 4096 rows x 65536, 2 sweeps, %.1f s" % dt}
+    return base, orc
+
+
+def run_b200(a):
+    import torch
+    import torch.distributed as dist
+    import numpy as np
+    from ising_gpu_b200.slab import SlabEngine
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != a.gpus and world > 1:
+        raise SystemExit("--gpus %d but WORLD_SIZE=%d" % (a.gpus, world))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    rows = a.rows_per_gpu or default_rows(world)
+    S = a.sweeps_per_step
+    eng = SlabEngine(X_COLS, rows, TEMP, a.seed, rank=rank, world=world, device=local, overlap=not a.no_overlap)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    eng.init_lattice()
+    for _ in range(a.warmup):
+        eng.sweeps(S)
+    sampler = ClockSampler(local) if rank == 0 else None
+    launches0 = eng.eng.launches
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(a.steps):
+        eng.sweeps(S)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = eng.eng.launches - launches0
+    clocks = sampler.stop() if sampler else None
+    if world > 1:
+        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    up, dn = eng.count_spins()
+    flips_per_rank = float(X_COLS) * rows * S * a.steps
+    value = flips_per_rank * world / (ms * 1e6)
+
+    # ---- end to end through the C ABI with host buffers ------------------------------------
+    e2e = None
+    if not a.no_e2e:
+        pitch = X_COLS // 64
+        hb = torch.empty((rows, pitch), dtype=torch.int32).pin_memory()
+        hw = torch.empty((rows, pitch), dtype=torch.int32).pin_memory()
+        nb, nw = hb.numpy().view(np.uint32), hw.numpy().view(np.uint32)
+        b0, w0 = eng.eng.export_bits()
+        nb[:], nw[:] = b0, w0
+        del b0, w0
+        ksteps = max(1, min(a.steps, a.e2e_steps))
+
+        def e2e_step():
+            eng.eng.import_bits(nb, nw)          # H2D of both colour planes (pinned)
+            if world > 1:
+                for color in (0, 1):              # ghost rows belong to the uploaded state
+                    eng._exchange_blocking(color)
+            eng.sweeps(S)
+            eng.eng._ck(eng.eng._L.ising_export_bits(eng.eng._h, 0, nb.ctypes.data, nw.ctypes.data))  # D2H
+            return eng.count_spins()              # D2H of the step's observable
+
+        e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(ksteps):
+            e2e_step()
+        barrier()
+        dt = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([dt], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        plane_bytes = rows * pitch * 4
+        e2e = {"value": round(float(X_COLS) * rows * S * ksteps * world / (dt * 1e9), 2), "unit": "flips/ns",
+               "h2d_bytes_per_step": 2 * plane_bytes * world, "d2h_bytes_per_step": (2 * plane_bytes + 16) * world,
+               "steps": ksteps, "api": "ising_import_bits + ising_update_color_part* + ising_export_bits + "
+                                       "ising_count_spins (C ABI, pinned host buffers)"}
+
+    out = None
+    if rank == 0:
+        peak, peak_src = measured_peaks()
+        half_sweeps = 2 * S * a.steps
+        kern_ms = ms / half_sweeps                         # one colour half-sweep on one GPU
+        alg_bytes = float(X_COLS) * rows / 2 * ALG_BYTES_PER_FLIP
+        achieved = alg_bytes / (kern_ms * 1e-3) / 1e9
+        roof = {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
+                "frac": round(achieved / peak, 4), "traffic": ncu_traffic_per_launch(),
+                "kernel": eng.eng.kernel_name, "kernel_ms": round(kern_ms, 4),
+                "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
+                "reference_accounting_gbs": round(achieved * REF_BYTES_PER_FLIP / ALG_BYTES_PER_FLIP, 1),
+                "note": "HBM-nominal path, but the bit-exact Philox4x32-10 per site makes it bound by the "
+                        "FMA-heavy pipe (IMAD.WIDE, 4 cycles/warp-instr): see DESIGN.md and profiles/"}
+        out = {"metric": "spin-flip attempts/ns", "value": round(value, 2), "unit": "flips/ns", "n_gpus": world,
+               "steps": a.steps, "warmup": a.warmup, "ms_per_step": round(ms / a.steps, 4), "higher_is_better": True,
+               "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+               "config": {"workload": "checkerboard Metropolis, %dx%d lattice (%d rows per GPU), T=%.1f, seed %d, "
+                                      "%d sweeps per step" % (rows * world, X_COLS, rows, TEMP, a.seed, S),
+                          "lattice_bytes_per_gpu": rows * X_COLS // 8, "l2_flush": "inputs larger than L2 "
+                          "(%d MiB of spins per GPU vs 126 MB L2)" % (rows * X_COLS // 8 >> 20),
+                          "halo": "none" if world == 1 else ("NCCL send/recv of 1 row per direction per colour, "
+                                  + ("overlapped with the interior update" if not a.no_overlap else "serialised"))},
+               "roofline": roof, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+               "final_counts": {"up": up if world == 1 else None, "down": dn if world == 1 else None}}
+        if world == 1 and not a.no_cpu:
+            out["cpu_baseline"], out["cpu_oracle"] = cpu_baselines()
+    if world > 1:
+        # total spin counts as a cross-rank checksum
+        t = torch.tensor([up, dn], device="cuda", dtype=torch.int64)
+        dist.all_reduce(t)
+        if rank == 0:
+            out["final_counts"] = {"up": int(t[0]), "down": int(t[1])}
+        dist.barrier()
+        dist.destroy_process_group()
+    eng.close()
+    if rank == 0:
+        print(json.dumps(out), flush=True)
+
+
+def run_reference(a):
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n = max(world, a.gpus)
+    rows = a.rows_per_gpu or default_rows(n)
+    S = a.sweeps_per_step
+    binary = os.path.join(ROOT, "oracle", "_ref", "cuIsing_ref")
+    base = {"metric": "spin-flip attempts/ns", "unit": "flips/ns", "n_gpus": n, "steps": a.steps, "warmup": a.warmup,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "data": "synthetic", "impl": "reference",
+            "config": {"workload": "checkerboard Metropolis, %dx%d lattice (%d rows per GPU), T=%.1f, seed %d, "
+                                   "%d sweeps per step" % (rows * n, X_COLS, rows, TEMP, a.seed, S)}}
+    try:
+        have_gpu = subprocess.run(["nvidia-smi", "-L"], capture_output=True).returncode == 0
+    except OSError:
+        have_gpu = False
+    if os.access(binary, os.X_OK) and have_gpu and not a.ref_cpu:
+        # the reference has no warm-up option: run the warm-up sweeps as a separate short run
+        def call(nsweeps):
+            cmd = [binary, "-x", str(X_COLS), "-y", str(rows), "-n", str(nsweeps), "-t", str(TEMP), "-s", str(a.seed),
+                   "-d", str(n)]
+            r = subprocess.run(cmd, capture_output=True, text=True, timeout=1500)
+            m = re.search(r"Kernel execution time for (\d+) update steps: (\S+) ms, (\S+) flips/ns", r.stdout)
+            if not m:
+                raise RuntimeError("reference run failed: " + (r.stderr or r.stdout)[-400:])
+            fin = re.search(r"Final\s+magnetization:\s+\S+, up_s:\s+(\d+), dw_s:\s+(\d+)", r.stdout)
+            return float(m.group(2)), float(m.group(3)), (int(fin.group(1)), int(fin.group(2))) if fin else None
+        try:
+            if a.warmup:
+                call(max(1, a.warmup))
+            ms, fl, fin = call(S * a.steps)
+            base.update({"value": fl, "ms_per_step": round(ms / a.steps, 4), "dtype": "u64 (4 bit/spin)",
+                         "reference_kind": "unmodified optimized/main.cu + utils.c, nvcc -O3 --use_fast_math for "
+                                           "sm_100a, run through its own CLI (cuIsing_ref -d %d)" % n,
+                         "final_counts": {"up": fin[0], "down": fin[1]} if fin else None,
+                         "cpu_baseline": {"value": fl, "unit": "flips/ns", "cores": 0, "kind": "reference",
+                                          "sample": "GPU reference binary, not a CPU run: %d sweeps of the full "
+                                                    "workload" % (S * a.steps)},
+                         "e2e": {"value": fl, "unit": "flips/ns", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
+            print(json.dumps(base), flush=True)
+            return
+        except Exception as e:   # fall through to the CPU port
+            base["reference_gpu_error"] = str(e)[:300]
+    # CPU fallback: the bit-exact oracle port on all host cores, bounded sample of the workload
+    from oracle import ising_oracle
+    srows = 2048
+    L = ising_oracle.OracleLattice(X_COLS, srows)
+    L.init()
+    for _ in range(min(a.warmup, 1)):
+        L.sweeps(1, TEMP)
+    t0 = time.perf_counter()
+    for _ in range(a.steps):
+        L.sweeps(1, TEMP)
+    dt = time.perf_counter() - t0
+    fl = X_COLS * srows * a.steps / dt * 1e-9
+    base.update({"value": round(fl, 4), "ms_per_step": round(dt * 1e3 / a.steps, 3), "dtype": "u8",
+                 "cpu_baseline": {"value": round(fl, 4), "unit": "flips/ns", "cores": ising_oracle.num_threads(),
+                                  "kind": "port", "sample": "C/OpenMP oracle, %d rows x %d, 1 sweep per step" %
+                                  (srows, X_COLS)},
+                 "e2e": {"value": round(fl, 4), "unit": "flips/ns", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
+    print(json.dumps(base), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--sweeps-per-step", type=int, default=16)
+    ap.add_argument("--rows-per-gpu", type=int, default=0)
+    ap.add_argument("--seed", type=int, default=463463564571)
+    ap.add_argument("--e2e-steps", type=int, default=4)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-overlap", action="store_true")
+    ap.add_argument("--ref-cpu", action="store_true", help="reference arm: force the CPU oracle port")
+    a = ap.parse_args()
+    if a.warmup < 3 and a.impl == "b200":
+        a.warmup = 3   # timing rule: at least 3 warm-up steps
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        if a.gpus > 1 and int(os.environ.get("WORLD_SIZE", "1")) == 1:
+            raise SystemExit("for --gpus N>1 launch with torchrun (one rank per GPU)")
+        run_b200(a)
+
+
+if __name__ == "__main__":
+    main()

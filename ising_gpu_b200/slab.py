@@ -1,0 +1,137 @@
+"""One-process-per-GPU slab decomposition: the lattice is cut into `world` slabs of Y rows
+(rows [r*Y, (r+1)*Y) on rank r, ring-periodic), exactly the reference's -d decomposition
+(optimized/main.cu:1542-1545, :1773; ring wrap slY = Y*ndev :1459).  The reference lets edge
+blocks read the neighbour GPU's boundary row through managed memory (loadTile, :413-428) behind
+a host barrier per colour (:1779-1784); here every slab keeps two ghost rows per colour, and
+after each colour update the freshly written first/last row travels to the neighbours' ghost
+rows (one X/16-byte message per direction) while the interior tiles are still being updated.
+
+`HaloExchange` is transport + ordering only and is backend-agnostic: a backend exposes
+    edge_rows(color)  -> (first_row, last_row)    1-D tensors to send
+    ghost_rows(color) -> (top_ghost, bottom_ghost) 1-D tensors to receive into
+    update(color, it, part)                         part in {ALL, EDGES, INTERIOR}
+On GPUs the tensors alias the library's device memory and travel over NCCL (NVLink); the CPU
+tests drive the same class over gloo with the oracle as backend.
+"""
+import torch
+import torch.distributed as dist
+
+from .engine import F_NO_PEER_COPY, PART_ALL, PART_EDGES, PART_INTERIOR, IsingEngine
+
+
+class HaloExchange:
+    def __init__(self, rank, world, group=None):
+        self.rank, self.world, self.group = rank, world, group
+        self.up = (rank - 1) % world      # owns the rows above mine
+        self.down = (rank + 1) % world    # owns the rows below mine
+
+    def start(self, backend, color):
+        """Post the 4 messages of one colour.  Returns the request list (wait() before the ghosts
+        are read).  Message order is fixed so that with world == 2 (up == down) the two rows
+        exchanged with the single peer are matched unambiguously: first rows go first."""
+        if self.world == 1:
+            return []
+        first, last = backend.edge_rows(color)
+        top, bottom = backend.ghost_rows(color)
+        ops = [dist.P2POp(dist.isend, first, self.up, self.group),      # my row 0   -> their bottom ghost
+               dist.P2POp(dist.isend, last, self.down, self.group),     # my row Y-1 -> their top ghost
+               dist.P2POp(dist.irecv, bottom, self.down, self.group),   # their row 0   -> my bottom ghost
+               dist.P2POp(dist.irecv, top, self.up, self.group)]        # their row Y-1 -> my top ghost
+        return dist.batch_isend_irecv(ops)
+
+    @staticmethod
+    def finish(reqs):
+        for r in reqs:
+            r.wait()
+
+
+class _DevRows:
+    """Zero-copy torch view of one device row of the library's lattice."""
+
+    def __init__(self, ptr, nbytes):
+        self.__cuda_array_interface__ = {"shape": (nbytes // 4,), "typestr": "<i4", "data": (ptr, False),
+                                         "version": 2}
+
+
+class GpuSlab:
+    """Backend over libising_b200.so for one rank (one GPU)."""
+
+    def __init__(self, X, Y, rank, world, device, temp, seed, stream):
+        self.eng = IsingEngine(X, Y, ndev=1, seed=seed, temp=temp, first_device=device, slab_first=rank,
+                               slab_count=world, flags=F_NO_PEER_COPY if world > 1 else 0)
+        self.eng.set_stream(0, stream.cuda_stream)
+        self.Y = Y
+        self._rows = {}
+        if world > 1:
+            dev = torch.device("cuda", device)
+            for color in (0, 1):
+                for row in (-1, 0, Y - 1, Y):
+                    ptr, n = self.eng.row_ptr(0, color, row)
+                    self._rows[(color, row)] = torch.as_tensor(_DevRows(ptr, n), device=dev)
+
+    def edge_rows(self, color):
+        return self._rows[(color, 0)], self._rows[(color, self.Y - 1)]
+
+    def ghost_rows(self, color):
+        return self._rows[(color, -1)], self._rows[(color, self.Y)]
+
+    def update(self, color, it, part=PART_ALL, stream=None):
+        self.eng.update_color_part(0, color, it, part, stream.cuda_stream if stream is not None else None)
+
+
+class SlabEngine:
+    """What bench.py and the multi-GPU tests drive: init + sweeps with overlapped halo exchange."""
+
+    def __init__(self, X, Y, temp, seed, rank=0, world=1, device=0, group=None, overlap=True):
+        self.rank, self.world, self.overlap = rank, world, overlap
+        torch.cuda.set_device(device)
+        self.main = torch.cuda.current_stream()
+        self.comm = torch.cuda.Stream() if world > 1 else None
+        self.slab = GpuSlab(X, Y, rank, world, device, temp, seed, self.main)
+        self.eng = self.slab.eng
+        self.halo = HaloExchange(rank, world, group)
+        self.it = 0
+        self._ev_edges = torch.cuda.Event()
+        self._ev_comm = torch.cuda.Event()
+
+    def _exchange_blocking(self, color):
+        HaloExchange.finish(self.halo.start(self.slab, color))
+
+    def init_lattice(self):
+        self.eng.init_lattice()
+        self.it = 0
+        if self.world > 1:
+            for color in (0, 1):
+                self._exchange_blocking(color)
+
+    def _half_sweep(self, color, it):
+        if self.world == 1:
+            self.slab.update(color, it, PART_ALL)
+            return
+        if not self.overlap:
+            self.slab.update(color, it, PART_ALL)
+            self._exchange_blocking(color)
+            return
+        # edges first, then ship them while the interior runs
+        self.main.wait_event(self._ev_comm)            # ghosts of the other colour have landed
+        self.slab.update(color, it, PART_EDGES)
+        self._ev_edges.record(self.main)
+        with torch.cuda.stream(self.comm):
+            self.comm.wait_event(self._ev_edges)
+            HaloExchange.finish(self.halo.start(self.slab, color))
+            self._ev_comm.record(self.comm)
+        self.slab.update(color, it, PART_INTERIOR)
+
+    def sweeps(self, n):
+        for _ in range(n):
+            self.it += 1
+            self._half_sweep(0, self.it)
+            self._half_sweep(1, self.it)
+        if self.world > 1 and self.overlap:
+            self.main.wait_event(self._ev_comm)
+
+    def count_spins(self):
+        return self.eng.count_spins()
+
+    def close(self):
+        self.eng.close()

@@ -46,6 +46,10 @@ typedef struct {
     long long half;     /* X/2 = sites of one colour per row                              */
     uint8_t  *plane[2]; /* [0]=black, [1]=white, rows*half bytes each                     */
     uint8_t  *bond[2];  /* optional +-J bond nibbles per site (NULL when -J unused)       */
+    /* slab mode (multi-process tests): this object holds rows [grow0, grow0+rows) of a taller
+     * lattice; the rows just outside come from ghost buffers instead of the periodic wrap.    */
+    long long grow0;
+    uint8_t  *ghost_top[2], *ghost_bot[2];   /* per colour, half bytes each; NULL = periodic    */
 } ora_lattice;
 
 /* ---- Philox4x32-10: public algorithm (Salmon et al. 2011), as shipped in the CUDA
@@ -115,10 +119,24 @@ ora_lattice *ora_create(int X, long long rows, int xsl, long long ysl)
     return L;
 }
 
+/* Turn the object into a slab starting at global row grow0, with ghost rows (zeroed). */
+int ora_make_slab(ora_lattice *L, long long grow0)
+{
+    L->grow0 = grow0;
+    for (int c = 0; c < 2; c++) {
+        L->ghost_top[c] = (uint8_t *)calloc((size_t)L->half, 1);
+        L->ghost_bot[c] = (uint8_t *)calloc((size_t)L->half, 1);
+        if (!L->ghost_top[c] || !L->ghost_bot[c]) return -1;
+    }
+    return 0;
+}
+uint8_t *ora_ghost(ora_lattice *L, int color, int bottom) { return bottom ? L->ghost_bot[color] : L->ghost_top[color]; }
+
 void ora_destroy(ora_lattice *L)
 {
     if (!L) return;
     free(L->plane[0]); free(L->plane[1]);
+    for (int c = 0; c < 2; c++) { free(L->ghost_top[c]); free(L->ghost_bot[c]); }
     free(L->bond[0]);  free(L->bond[1]);
     free(L);
 }
@@ -131,6 +149,7 @@ uint8_t *ora_plane(ora_lattice *L, int color) { return L->plane[color]; }
 static inline uint32_t ref_tid(const ora_lattice *L, long long r, long long c)
 {
     const uint32_t gridX = (uint32_t)(L->half / 32 / (REF_BDIM_X * REF_LOOP_X));
+    r += L->grow0;                                            /* global row of a slab's local row */
     const uint32_t brow  = (uint32_t)(r / REF_BDIM_Y);        /* devid*gridDim.y + blockIdx.y */
     const uint32_t bx    = (uint32_t)(c / (REF_BDIM_X * REF_LOOP_X));
     const uint32_t tx    = (uint32_t)(c % REF_BDIM_X);
@@ -216,6 +235,8 @@ void ora_update_color(ora_lattice *L, int color, unsigned long long seed, int it
         const uint8_t *up = src + (size_t)wrap_row(L, r, -1) * L->half;
         const uint8_t *ct = src + (size_t)r * L->half;
         const uint8_t *dw = src + (size_t)wrap_row(L, r, +1) * L->half;
+        if (r == 0 && L->ghost_top[color ^ 1]) up = L->ghost_top[color ^ 1];
+        if (r == L->rows - 1 && L->ghost_bot[color ^ 1]) dw = L->ghost_bot[color ^ 1];
         const int readBack = (color == 0) ? !(r & 1) : (int)(r & 1);
         for (long long c = 0; c < nwords; c++) {
             const int j = (int)((c % 32) / 16);

@@ -49,6 +49,9 @@ def lib():
     L.ora_import_bits.argtypes = [C.c_void_p, C.c_int, u32p]
     L.ora_dump.argtypes = [C.c_void_p, C.c_longlong, C.c_longlong, C.c_char_p]
     L.ora_num_threads.restype = C.c_int
+    L.ora_make_slab.argtypes = [C.c_void_p, C.c_longlong]
+    L.ora_ghost.argtypes = [C.c_void_p, C.c_int, C.c_int]
+    L.ora_ghost.restype = C.POINTER(C.c_uint8)
     L.ora_init_count.argtypes = [C.c_int, C.c_longlong, C.c_ulonglong]
     L.ora_init_count.restype = C.c_ulonglong
     _LIB = L
@@ -144,6 +147,16 @@ class OracleLattice:
         nrows = self.rows - row0 if nrows is None else nrows
         if lib().ora_dump(self._h, int(row0), int(nrows), os.fsencode(fname)) != 0:
             raise OSError("cannot write " + fname)
+
+    def make_slab(self, grow0):
+        """Hold rows [grow0, grow0+rows) of a taller lattice; edge neighbours come from ghost rows."""
+        if lib().ora_make_slab(self._h, int(grow0)) != 0:
+            raise MemoryError
+        self.is_slab = True
+
+    def ghost(self, color, bottom):
+        p = lib().ora_ghost(self._h, int(color), int(bool(bottom)))
+        return np.ctypeslib.as_array(p, shape=(self.X // 2,))
 
     def lattice(self):
         """Full rows x X array of 0/1 in true lattice order (dumpLattice interleave)."""

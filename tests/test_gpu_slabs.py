@@ -1,0 +1,102 @@
+"""GPU tests of the slab decomposition: ghost rows, edge/interior split, single-process -d N and
+one-process-per-GPU over NCCL.  Property under test (optimized/main.cu:514-515, README -d runs):
+N slabs of Y rows give exactly the lattice of one device with N*Y rows."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+TC = 2.269185
+
+
+def _ngpu():
+    import torch
+    return torch.cuda.device_count()
+
+
+def _oracle_planes(oracle, X, rows, sweeps, temp):
+    L = oracle.OracleLattice(X, rows)
+    L.init()
+    L.sweeps(sweeps, temp)
+    return L.export_bits(0), L.export_bits(1), L.count()
+
+
+@pytest.mark.parametrize("nslab,Y", [(2, 32), (3, 16), (4, 48)])
+def test_slabs_on_one_gpu_with_manual_halo(ig, oracle, nslab, Y):
+    """Several slab contexts on device 0, ghost rows copied by the test through ising_row_ptr:
+    exercises the ghost-row addressing and the EDGES / INTERIOR launches without needing 2 GPUs."""
+    import torch
+    from ising_gpu_b200.engine import F_NO_PEER_COPY, PART_EDGES, PART_INTERIOR
+    from ising_gpu_b200.slab import _DevRows
+    X, sweeps = 4096, 3
+    engs = [ig.IsingEngine(X, Y, temp=TC, slab_first=s, slab_count=nslab, flags=F_NO_PEER_COPY) for s in range(nslab)]
+    dev = torch.device("cuda", 0)
+
+    def row(e, color, r):
+        p, n = e.row_ptr(0, color, r)
+        return torch.as_tensor(_DevRows(p, n), device=dev)
+
+    def exchange(color):
+        for e in engs:
+            e.sync()
+        for s, e in enumerate(engs):
+            up, dn = engs[(s - 1) % nslab], engs[(s + 1) % nslab]
+            row(up, color, Y).copy_(row(e, color, 0))          # my first row -> bottom ghost of the slab above
+            row(dn, color, -1).copy_(row(e, color, Y - 1))     # my last row  -> top ghost of the slab below
+        torch.cuda.synchronize()
+
+    for e in engs:
+        e.init_lattice()
+    exchange(0); exchange(1)
+    for it in range(1, sweeps + 1):
+        for color in (0, 1):
+            for e in engs:
+                e.update_color_part(0, color, it, PART_EDGES)
+                e.update_color_part(0, color, it, PART_INTERIOR)
+            exchange(color)
+    ob, ow, cnt = _oracle_planes(oracle, X, Y * nslab, sweeps, TC)
+    gb = np.vstack([e.export_bits()[0] for e in engs])
+    gw = np.vstack([e.export_bits()[1] for e in engs])
+    assert np.array_equal(gb, ob) and np.array_equal(gw, ow)
+    ups = sum(e.count_spins()[0] for e in engs)
+    assert ups == cnt[0]
+    for e in engs:
+        e.close()
+
+
+def test_single_process_two_devices(ig, oracle):
+    """cuIsing -d 2 path: one context, two GPUs, library-managed peer copies."""
+    if _ngpu() < 2:
+        pytest.skip("needs 2 GPUs")
+    X, Y, sweeps = 4096, 64, 4
+    with ig.IsingEngine(X, Y, ndev=2, temp=TC) as eng:
+        eng.init_lattice()
+        eng.sweeps(sweeps)
+        ob, ow, cnt = _oracle_planes(oracle, X, 2 * Y, sweeps, TC)
+        gb = np.vstack([eng.export_bits(d)[0] for d in range(2)])
+        gw = np.vstack([eng.export_bits(d)[1] for d in range(2)])
+        assert np.array_equal(gb, ob) and np.array_equal(gw, ow)
+        assert eng.count_spins() == cnt
+
+
+@pytest.mark.parametrize("overlap", [1, 0])
+def test_one_process_per_gpu_nccl(oracle, tmp_path, overlap):
+    """torchrun, 2 ranks, NCCL halo (overlapped and serialised): stacked slabs == oracle."""
+    if _ngpu() < 2:
+        pytest.skip("needs 2 GPUs")
+    X, Y, sweeps = 4096, 64, 5
+    out = tmp_path / "slabs"
+    out.mkdir()
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr",
+           "127.0.0.1", "--master-port", "29533", os.path.join(ROOT, "tests", "slab_worker.py"), str(X), str(Y),
+           str(sweeps), str(TC), str(overlap), str(out)]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    ob, ow, cnt = _oracle_planes(oracle, X, 2 * Y, sweeps, TC)
+    gb = np.vstack([np.load(out / ("b%d.npy" % k)) for k in range(2)])
+    gw = np.vstack([np.load(out / ("w%d.npy" % k)) for k in range(2)])
+    assert np.array_equal(gb, ob) and np.array_equal(gw, ow)
