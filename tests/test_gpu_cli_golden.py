@@ -1,0 +1,35 @@
+"""GPU: the cuIsing command-line host (C++ over the C ABI) against the golden transcripts and
+dump files of the reference binary: same options -> same magnetization lines, same files."""
+import os
+import subprocess
+
+import pytest
+
+import golden_util as G
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CLI = os.path.join(ROOT, "ising_gpu_b200", "cuIsing")
+
+CASES = ["small_T1.5", "small_Tc", "rag_Tc", "sub_T1.5", "alpha_default", "seed_T2", "ramp", "mid_T1.5", "mid_Tc",
+         "big_Tc", "big_T1.5", "big_sub_T1.5", "expser", "magn_stop"]
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_cli_matches_reference_transcript(case, tmp_path):
+    c = G.cases()[case]
+    r = subprocess.run([CLI] + c["args"], cwd=tmp_path, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stderr[-1000:]
+    mine = [ln for ln in r.stdout.splitlines()
+            if "magnetization" in ln or ln.startswith("Changing temperature") or ln.startswith("exp[")]
+    assert mine == c["lines"]
+    gold = G.extract_files(case, str(tmp_path / "gold"))
+    for name, path in gold.items():
+        assert (tmp_path / name).exists(), "missing dump " + name
+        assert (tmp_path / name).read_bytes() == open(path, "rb").read(), name
+    assert "flips/ns" in r.stdout
+
+
+def test_cli_bad_dims_prints_usage_and_exits_zero(tmp_path):
+    r = subprocess.run([CLI, "-x", "100"], cwd=tmp_path, capture_output=True, text=True)
+    assert r.returncode == 0 and "Please specify an X dim multiple of 2048" in r.stderr and "Usage:" in r.stdout
