@@ -9,8 +9,8 @@ CLI     := ising_gpu_b200/cuIsing
 
 all: $(LIB) $(CLI) oracle
 
-$(LIB): $(CSRC)/kernels.cu $(CSRC)/ising_api.cu $(CSRC)/kernels.cuh $(CSRC)/philox_map.h $(CSRC)/host_math.h include/ising_b200.h
-	$(NVCC) $(NVFLAGS) -shared -o $@ $(CSRC)/kernels.cu $(CSRC)/ising_api.cu
+$(LIB): $(CSRC)/kernels.cu $(CSRC)/ising_api.cu $(CSRC)/tc_variant.cu $(CSRC)/kernels.cuh $(CSRC)/philox_map.h $(CSRC)/host_math.h include/ising_b200.h
+	$(NVCC) $(NVFLAGS) -shared -o $@ $(CSRC)/kernels.cu $(CSRC)/ising_api.cu $(CSRC)/tc_variant.cu
 
 $(CLI): $(CSRC)/cuising_main.cpp $(LIB) include/ising_b200.h
 	$(NVCC) -O2 -std=c++17 -Xcompiler -Wall -o $@ $(CSRC)/cuising_main.cpp -Iinclude -Lising_gpu_b200 -lising_b200 -Xlinker -rpath -Xlinker '$$ORIGIN'

@@ -173,6 +173,47 @@ uint64_t ising_launch_count(const ising_ctx* ctx);
 /* name of the update kernel variant in use, for logs */
 const char* ising_kernel_name(const ising_ctx* ctx);
 
+/* ==========================================================================================
+ * Tensor-core variant: drop-in for the hot path of the reference's tensorcore/ program
+ * (tensorcore/main.cu): +-1 lattice in 256x256 super-blocks of four 128x128 sub-blocks
+ * (:37-44), neighbour sums as matrix products with a bidiagonal 0/1 matrix (:252-262, :547-569)
+ * plus block-edge terms (add_boundaries :148-226), Metropolis with its own RNG map
+ * (update_spins :88-146, init_spins :63-79).  Here the sums are an INT8 tensor-core
+ * contraction fused with the update in one kernel; nn_sums is never written to memory.
+ * ========================================================================================== */
+typedef struct ising_tc_ctx ising_tc_ctx;
+
+enum { ISING_TC_NN_MMA = 0,     /* INT8 tensor-core contraction (product path)                 */
+       ISING_TC_NN_STENCIL = 1  /* plain integer 4-neighbour stencil (validation of the MMA)   */ };
+
+/* nbx, nby: lattice columns / rows in units of 256 (-x, -y of ising_tensorcore, main.cu:402-451);
+ * alpha: temperature in T_crit units (-a); seed (-s, default 1234). */
+int ising_tc_create(int nbx, int nby, uint64_t seed, float alpha, int device, ising_tc_ctx** out);
+int ising_tc_destroy(ising_tc_ctx* ctx);
+int ising_tc_set_nn_path(ising_tc_ctx* ctx, int path);
+/* init_spins (main.cu:492-497) */
+int ising_tc_init(ising_tc_ctx* ctx);
+/* n calls of update() (main.cu:237-298) with iteration numbers first_iter .. first_iter+n-1
+ * (the reference numbers warm-up and trial iterations consecutively from 1, :582-593). Async. */
+int ising_tc_update(ising_tc_ctx* ctx, uint64_t first_iter, int n);
+int ising_tc_update_timed(ising_tc_ctx* ctx, uint64_t first_iter, int n, float* ms);
+int ising_tc_sync(ising_tc_ctx* ctx);
+/* sum of all spins (the reference's final CUB reduce, main.cu:611-636) */
+int ising_tc_sum(ising_tc_ctx* ctx, int64_t* sum);
+/* lattice as int8 +-1: storage (blocked) order, or true row-major order ny x nx (main.cu:317-336) */
+int ising_tc_export_storage(ising_tc_ctx* ctx, int8_t* out);
+int ising_tc_import_storage(ising_tc_ctx* ctx, const int8_t* in);
+int ising_tc_export_true(ising_tc_ctx* ctx, int8_t* out);
+/* write_lattice (main.cu:300-352): "<spin> " per site, one line per row */
+int ising_tc_write_lattice(ising_tc_ctx* ctx, const char* fname);
+/* the five acceptance values exp(-2*inv_temp*v), v = nn*s = -4,-2,0,2,4, evaluated on the device
+ * with the same expf the reference's update_spins uses (main.cu:137) */
+int ising_tc_accept_table(ising_tc_ctx* ctx, float out[5]);
+/* neighbour sums of one colour in storage order (0 elsewhere) as the selected nn path computes
+ * them -- what main.cu:252-266 leaves in nn_sums; for tests */
+int ising_tc_neighbour_sums(ising_tc_ctx* ctx, int is_black, int8_t* out);
+uint64_t ising_tc_launch_count(const ising_tc_ctx* ctx);
+
 #ifdef __cplusplus
 }
 #endif

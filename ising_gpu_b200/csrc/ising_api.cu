@@ -188,6 +188,9 @@ int push_halo(ising_ctx* c, int color)
 
 extern "C" {
 
+// shared by the tensor-core variant's translation unit (not part of the public header)
+void ising_internal_set_error(const char* msg) { g_err = msg ? msg : ""; }
+
 const char* ising_last_error(void) { return g_err.c_str(); }
 int ising_abi_version(void) { return ISING_B200_ABI_VERSION; }
 uint64_t ising_accept_count(float p, int strict) { return accept_count(p, strict != 0); }

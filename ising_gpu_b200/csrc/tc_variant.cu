@@ -1,0 +1,431 @@
+// tc_variant.cu -- tensor-core variant of the Metropolis update: B200-native replacement of
+// the hot path of the reference's tensorcore/ program (tensorcore/main.cu: init_spins :63-79,
+// 4x cublasGemmBatchedEx :252-262/:277-287, add_boundaries :148-226, update_spins :88-146).
+//
+// The reference materialises the neighbour sums: per colour two batched fp16 GEMMs write
+// nn_sums (2 GiB at 32768^2), a third kernel patches the sub-block edges, a fourth reads
+// nn_sums back and flips spins.  Here one kernel per colour owns a 128x128 sub-block per CTA,
+// forms its neighbour sums on the tensor cores as an INT8 contraction with the bidiagonal 0/1
+// matrices, keeps them on chip, adds the edge terms and does the Metropolis step -- nn_sums
+// never exists in memory and the lattice is int8 (+-1) instead of fp16.
+//
+// Contract kept bit for bit: the blocked storage order, the element -> (Philox subsequence,
+// offset) map of update_spins/init_spins, the acceptance test `uniform < exp(-2 b nn s)` with
+// the DEVICE expf (evaluated once per temperature, turned into integer thresholds on the host),
+// and the final.txt format.
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "../../include/ising_b200.h"
+#include "host_math.h"
+#include "philox_map.h"
+
+using namespace ising;
+
+namespace {
+
+constexpr int SUPN = 256;   // LATTICE_SUP_N
+constexpr int SUBN = 128;   // LATTICE_SUB_N
+constexpr int TPS = SUBN * SUBN / 16;   // reference threads per sub-block (NLOOPS*SPINSPERTHREAD = 16)
+
+struct TcParams {
+    int nbx, nby;
+    uint32_t key0, key1;
+    uint64_t call0;          // Philox counter of the first of the 4 calls: 4*(2*iter + colour)
+    uint32_t thr[5];         // accept iff x <= thr[k], k = (nn*s+4)/2 ...
+    uint32_t always[5];      // ... or always[k] (all ones), and never if never[k]
+    uint32_t never[5];
+    int is_black;
+};
+
+__host__ __device__ __forceinline__ long long sup_offset(long long i, long long j, long long nbx)
+{
+    return (j * nbx + i) * SUPN * SUPN;
+}
+__host__ __device__ __forceinline__ long long sub_offset(int a, int b) { return ((long long)b * SUPN + (long long)a * SUBN) * SUBN; }
+
+// spin of sub-block kind (a,b) at element (i,j) of super-block (sx,sy), with i/j allowed to step
+// one element outside [0,128): continues in the periodic neighbour super-block.
+__device__ __forceinline__ int spin_at(const int8_t* __restrict__ lat, int nbx, int nby, int sx, int sy, int a, int b,
+                                       int i, int j)
+{
+    if (i < 0) { i += SUBN; sx = (sx == 0) ? nbx - 1 : sx - 1; }
+    if (i >= SUBN) { i -= SUBN; sx = (sx == nbx - 1) ? 0 : sx + 1; }
+    if (j < 0) { j += SUBN; sy = (sy == 0) ? nby - 1 : sy - 1; }
+    if (j >= SUBN) { j -= SUBN; sy = (sy == nby - 1) ? 0 : sy + 1; }
+    return lat[sup_offset(sx, sy, nbx) + sub_offset(a, b) + (long long)j * SUBN + i];
+}
+
+// which sub-block does CTA `sb` of this colour own (update_spins :99-124)
+__device__ __forceinline__ void block_of(int sb, int nbx, bool black, int& bi, int& bj)
+{
+    bi = sb % (2 * nbx);
+    const int h = sb / (2 * nbx);
+    bj = black ? ((bi & 1) ? 2 * h + 1 : 2 * h) : ((bi & 1) ? 2 * h : 2 * h + 1);
+}
+
+// ------------------------------------------------------------------------------------------
+// Validation path: integer stencil.  One CTA per sub-block, thread j owns row j (128 spins).
+// ------------------------------------------------------------------------------------------
+template <bool WRITE_NN>
+__global__ void __launch_bounds__(SUBN) tc_update_stencil_kernel(int8_t* __restrict__ lat, int8_t* __restrict__ nn_out,
+                                                                 const __grid_constant__ TcParams p)
+{
+    const int sb = blockIdx.x, j = threadIdx.x;
+    int bi, bj;
+    block_of(sb, p.nbx, p.is_black != 0, bi, bj);
+    const int a = bi & 1, b = bj & 1, sx = bi >> 1, sy = bj >> 1;
+    const long long base = sup_offset(sx, sy, p.nbx) + sub_offset(a, b);
+    const int di = (a == 0) ? -1 : +1, dj = (b == 0) ? -1 : +1;
+
+    for (int c = 0; c < 16; c++) {
+        const int lin = 16 * j + c, n = lin / TPS, tl = lin % TPS;
+        const uint64_t tid = (uint64_t)sb * TPS + (uint64_t)tl;
+        int8_t s[8];
+        *reinterpret_cast<uint2*>(s) = *reinterpret_cast<const uint2*>(lat + base + (long long)j * SUBN + 8 * c);
+        uint32_t o[8];
+        for (int h = 0; h < 2; h++) {
+            const uint64_t ctr = p.call0 + 2 * n + h;
+            philox4x32_10((uint32_t)ctr, (uint32_t)(ctr >> 32), (uint32_t)tid, (uint32_t)(tid >> 32), p.key0, p.key1,
+                          o + 4 * h);
+        }
+#pragma unroll
+        for (int m = 0; m < 8; m++) {
+            const int i = 8 * c + m;
+            const int nn = spin_at(lat, p.nbx, p.nby, sx, sy, 1 - a, b, i, j) + spin_at(lat, p.nbx, p.nby, sx, sy, 1 - a, b, i + di, j) +
+                           spin_at(lat, p.nbx, p.nby, sx, sy, a, 1 - b, i, j) + spin_at(lat, p.nbx, p.nby, sx, sy, a, 1 - b, i, j + dj);
+            if (WRITE_NN) {
+                nn_out[base + (long long)j * SUBN + i] = (int8_t)nn;
+            } else {
+                const int k = (nn * s[m] + 4) >> 1;
+                const bool flip = p.always[k] || (!p.never[k] && o[m] <= p.thr[k]);
+                if (flip) s[m] = (int8_t)-s[m];
+            }
+        }
+        if (!WRITE_NN) *reinterpret_cast<uint2*>(lat + base + (long long)j * SUBN + 8 * c) = *reinterpret_cast<uint2*>(s);
+    }
+}
+
+// init_spins: element t <- first output of Philox(subsequence t, offset 0); uniform < 0.5 -> -1
+__global__ void __launch_bounds__(256) tc_init_kernel(int8_t* __restrict__ lat, long long n, uint32_t key0, uint32_t key1,
+                                                     uint32_t thr_half)
+{
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x) {
+        uint32_t o[4];
+        philox4x32_10(0u, 0u, (uint32_t)t, (uint32_t)((unsigned long long)t >> 32), key0, key1, o);
+        lat[t] = (o[0] <= thr_half) ? -1 : 1;
+    }
+}
+
+// exp(-2 * inv_temp * v) for v = -4..4, with the device expf (tensorcore/main.cu:137)
+__global__ void tc_accept_kernel(float inv_temp, float* out)
+{
+    const int k = threadIdx.x;
+    if (k < 5) out[k] = exp(-2.0f * inv_temp * (float)(2 * k - 4));
+}
+
+__global__ void __launch_bounds__(256) tc_sum_kernel(const int8_t* __restrict__ lat, long long n, long long* out)
+{
+    long long acc = 0;
+    const char4* p4 = reinterpret_cast<const char4*>(lat);
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n / 4; t += (long long)gridDim.x * blockDim.x) {
+        const char4 v = p4[t];
+        acc += v.x + v.y + v.z + v.w;
+    }
+    for (int o = 16; o; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) atomicAdd(reinterpret_cast<unsigned long long*>(out), (unsigned long long)acc);
+}
+
+thread_local std::string g_tc_err;
+int tc_fail(int code, const char* fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_tc_err = buf;
+    return code;
+}
+#define TC_TRY(call)                                                                                        \
+    do {                                                                                                    \
+        cudaError_t e__ = (call);                                                                           \
+        if (e__ != cudaSuccess)                                                                             \
+            return tc_fail(ISING_ECUDA, "%s:%d: %s failed: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
+    } while (0)
+
+}  // namespace
+
+// the error string is shared with the main API through this hook (ising_api.cu)
+extern "C" void ising_internal_set_error(const char* msg);
+
+struct ising_tc_ctx {
+    int nbx = 0, nby = 0, device = 0, nn_path = ISING_TC_NN_STENCIL;
+    long long n = 0;
+    uint64_t seed = 0;
+    float alpha = 0, accept[5];
+    TcParams base{};
+    int8_t* lat = nullptr;
+    int8_t* scratch = nullptr;
+    long long* d_sum = nullptr;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    uint64_t launches = 0;
+};
+
+#define TC_RET(expr)                                       \
+    do {                                                   \
+        int rc__ = (expr);                                 \
+        if (rc__) ising_internal_set_error(g_tc_err.c_str()); \
+        return rc__;                                       \
+    } while (0)
+
+static int tc_create_impl(int nbx, int nby, uint64_t seed, float alpha, int device, ising_tc_ctx** out)
+{
+    if (!out || nbx <= 0 || nby <= 0) return tc_fail(ISING_EINVAL, "nbx and nby must be positive");
+    *out = nullptr;
+    TC_TRY(cudaSetDevice(device));
+    ising_tc_ctx* c = new ising_tc_ctx();
+    c->nbx = nbx; c->nby = nby; c->device = device; c->seed = seed; c->alpha = alpha;
+    c->n = (long long)nbx * nby * SUPN * SUPN;
+    cudaError_t e;
+    if ((e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess ||
+        (e = cudaMalloc(&c->lat, (size_t)c->n)) != cudaSuccess || (e = cudaMalloc(&c->d_sum, sizeof(long long))) != cudaSuccess ||
+        (e = cudaEventCreate(&c->e0)) != cudaSuccess || (e = cudaEventCreate(&c->e1)) != cudaSuccess) {
+        ising_tc_destroy(c);
+        return tc_fail(ISING_ECUDA, "tensor-core context: %s", cudaGetErrorString(e));
+    }
+    // acceptance values with the device expf, then exact integer thresholds
+    float* d_acc = nullptr;
+    TC_TRY(cudaMalloc(&d_acc, 5 * sizeof(float)));
+    const float inv_temp = 1.0f / (alpha * ISING_CRIT_TEMP);   // tensorcore/main.cu:578
+    tc_accept_kernel<<<1, 32, 0, c->stream>>>(inv_temp, d_acc);
+    TC_TRY(cudaMemcpyAsync(c->accept, d_acc, 5 * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    TC_TRY(cudaStreamSynchronize(c->stream));
+    TC_TRY(cudaFree(d_acc));
+    c->base.nbx = nbx; c->base.nby = nby;
+    c->base.key0 = (uint32_t)seed; c->base.key1 = (uint32_t)(seed >> 32);
+    for (int k = 0; k < 5; k++) {
+        const uint64_t n = accept_count(c->accept[k], true);   // uniform < accept (strict, main.cu:138)
+        c->base.always[k] = (n == (1ull << 32)) ? 0xffffffffu : 0u;
+        c->base.never[k] = (n == 0) ? 0xffffffffu : 0u;
+        c->base.thr[k] = (n == 0) ? 0u : (uint32_t)(n - 1);
+    }
+    *out = c;
+    return ISING_OK;
+}
+
+static int tc_launch_color(ising_tc_ctx* c, bool black, uint64_t iter, int8_t* nn_out)
+{
+    TcParams p = c->base;
+    p.is_black = black ? 1 : 0;
+    p.call0 = (2ull * iter + (black ? 0 : 1)) * 4ull;   // offset (2*iter [+1])*16 draws, main.cu:269/:294
+    const int ctas = 2 * c->nbx * c->nby;
+    if (nn_out) tc_update_stencil_kernel<true><<<ctas, SUBN, 0, c->stream>>>(c->lat, nn_out, p);
+    else        tc_update_stencil_kernel<false><<<ctas, SUBN, 0, c->stream>>>(c->lat, nullptr, p);
+    TC_TRY(cudaGetLastError());
+    c->launches++;
+    return ISING_OK;
+}
+
+extern "C" {
+
+int ising_tc_create(int nbx, int nby, uint64_t seed, float alpha, int device, ising_tc_ctx** out)
+{
+    TC_RET(tc_create_impl(nbx, nby, seed, alpha, device, out));
+}
+
+int ising_tc_destroy(ising_tc_ctx* c)
+{
+    if (!c) return ISING_OK;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    if (c->lat) cudaFree(c->lat);
+    if (c->scratch) cudaFree(c->scratch);
+    if (c->d_sum) cudaFree(c->d_sum);
+    if (c->e0) cudaEventDestroy(c->e0);
+    if (c->e1) cudaEventDestroy(c->e1);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+    return ISING_OK;
+}
+
+int ising_tc_set_nn_path(ising_tc_ctx* c, int path)
+{
+    if (!c || (path != ISING_TC_NN_MMA && path != ISING_TC_NN_STENCIL)) TC_RET(tc_fail(ISING_EINVAL, "bad nn path"));
+    c->nn_path = path;
+    return ISING_OK;
+}
+
+static int tc_init_impl(ising_tc_ctx* c)
+{
+    TC_TRY(cudaSetDevice(c->device));
+    const uint32_t thr_half = (uint32_t)(accept_count(0.5f, true) - 1);
+    tc_init_kernel<<<148 * 8, 256, 0, c->stream>>>(c->lat, c->n, c->base.key0, c->base.key1, thr_half);
+    TC_TRY(cudaGetLastError());
+    c->launches++;
+    return ISING_OK;
+}
+int ising_tc_init(ising_tc_ctx* c)
+{
+    if (!c) TC_RET(tc_fail(ISING_EINVAL, "null context"));
+    TC_RET(tc_init_impl(c));
+}
+
+static int tc_update_impl(ising_tc_ctx* c, uint64_t first_iter, int n)
+{
+    TC_TRY(cudaSetDevice(c->device));
+    for (int k = 0; k < n; k++) {
+        if (int rc = tc_launch_color(c, true, first_iter + k, nullptr)) return rc;
+        if (int rc = tc_launch_color(c, false, first_iter + k, nullptr)) return rc;
+    }
+    return ISING_OK;
+}
+int ising_tc_update(ising_tc_ctx* c, uint64_t first_iter, int n)
+{
+    if (!c || n < 0) TC_RET(tc_fail(ISING_EINVAL, "bad argument"));
+    TC_RET(tc_update_impl(c, first_iter, n));
+}
+
+static int tc_timed_impl(ising_tc_ctx* c, uint64_t first_iter, int n, float* ms)
+{
+    TC_TRY(cudaSetDevice(c->device));
+    TC_TRY(cudaStreamSynchronize(c->stream));
+    TC_TRY(cudaEventRecord(c->e0, c->stream));
+    if (int rc = tc_update_impl(c, first_iter, n)) return rc;
+    TC_TRY(cudaEventRecord(c->e1, c->stream));
+    TC_TRY(cudaEventSynchronize(c->e1));
+    TC_TRY(cudaEventElapsedTime(ms, c->e0, c->e1));
+    return ISING_OK;
+}
+int ising_tc_update_timed(ising_tc_ctx* c, uint64_t first_iter, int n, float* ms)
+{
+    if (!c || !ms || n < 0) TC_RET(tc_fail(ISING_EINVAL, "bad argument"));
+    TC_RET(tc_timed_impl(c, first_iter, n, ms));
+}
+
+static int tc_sync_impl(ising_tc_ctx* c)
+{
+    TC_TRY(cudaSetDevice(c->device));
+    TC_TRY(cudaStreamSynchronize(c->stream));
+    return ISING_OK;
+}
+int ising_tc_sync(ising_tc_ctx* c)
+{
+    if (!c) TC_RET(tc_fail(ISING_EINVAL, "null context"));
+    TC_RET(tc_sync_impl(c));
+}
+
+static int tc_sum_impl(ising_tc_ctx* c, int64_t* sum)
+{
+    TC_TRY(cudaSetDevice(c->device));
+    TC_TRY(cudaMemsetAsync(c->d_sum, 0, sizeof(long long), c->stream));
+    tc_sum_kernel<<<148 * 8, 256, 0, c->stream>>>(c->lat, c->n, c->d_sum);
+    TC_TRY(cudaGetLastError());
+    c->launches++;
+    long long h = 0;
+    TC_TRY(cudaMemcpyAsync(&h, c->d_sum, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+    TC_TRY(cudaStreamSynchronize(c->stream));
+    *sum = h;
+    return ISING_OK;
+}
+int ising_tc_sum(ising_tc_ctx* c, int64_t* sum)
+{
+    if (!c || !sum) TC_RET(tc_fail(ISING_EINVAL, "bad argument"));
+    TC_RET(tc_sum_impl(c, sum));
+}
+
+static int tc_copy_impl(ising_tc_ctx* c, int8_t* out, const int8_t* in)
+{
+    TC_TRY(cudaSetDevice(c->device));
+    if (out) TC_TRY(cudaMemcpyAsync(out, c->lat, (size_t)c->n, cudaMemcpyDeviceToHost, c->stream));
+    if (in) TC_TRY(cudaMemcpyAsync(c->lat, in, (size_t)c->n, cudaMemcpyHostToDevice, c->stream));
+    TC_TRY(cudaStreamSynchronize(c->stream));
+    return ISING_OK;
+}
+int ising_tc_export_storage(ising_tc_ctx* c, int8_t* out)
+{
+    if (!c || !out) TC_RET(tc_fail(ISING_EINVAL, "bad argument"));
+    TC_RET(tc_copy_impl(c, out, nullptr));
+}
+int ising_tc_import_storage(ising_tc_ctx* c, const int8_t* in)
+{
+    if (!c || !in) TC_RET(tc_fail(ISING_EINVAL, "bad argument"));
+    TC_RET(tc_copy_impl(c, nullptr, in));
+}
+
+// storage -> true order on the host (write_lattice, main.cu:317-336)
+static void to_true_order(const ising_tc_ctx* c, const int8_t* st, int8_t* out)
+{
+    const long long nx = (long long)c->nbx * SUPN;
+    for (int bj = 0; bj < c->nby; bj++)
+        for (int bi = 0; bi < c->nbx; bi++)
+            for (int b = 0; b < 2; b++)
+                for (int a = 0; a < 2; a++) {
+                    const int8_t* sub = st + sup_offset(bi, bj, c->nbx) + sub_offset(a, b);
+                    for (int j = 0; j < SUBN; j++)
+                        for (int i = 0; i < SUBN; i++)
+                            out[((long long)bj * SUPN + 2 * j + b) * nx + (long long)bi * SUPN + 2 * i + a] = sub[j * SUBN + i];
+                }
+}
+
+int ising_tc_export_true(ising_tc_ctx* c, int8_t* out)
+{
+    if (!c || !out) TC_RET(tc_fail(ISING_EINVAL, "bad argument"));
+    std::vector<int8_t> st((size_t)c->n);
+    if (int rc = tc_copy_impl(c, st.data(), nullptr)) TC_RET(rc);
+    to_true_order(c, st.data(), out);
+    return ISING_OK;
+}
+
+int ising_tc_write_lattice(ising_tc_ctx* c, const char* fname)
+{
+    if (!c || !fname) TC_RET(tc_fail(ISING_EINVAL, "bad argument"));
+    std::vector<int8_t> t((size_t)c->n);
+    if (int rc = ising_tc_export_true(c, t.data())) return rc;
+    FILE* f = fopen(fname, "w");
+    if (!f) TC_RET(tc_fail(ISING_EINVAL, "cannot open %s", fname));
+    const long long nx = (long long)c->nbx * SUPN, ny = (long long)c->nby * SUPN;
+    std::string line;
+    for (long long r = 0; r < ny; r++) {
+        line.clear();
+        for (long long col = 0; col < nx; col++) line += (t[(size_t)(r * nx + col)] > 0) ? "1 " : "-1 ";
+        line += "\n";
+        fwrite(line.data(), 1, line.size(), f);
+    }
+    fclose(f);
+    return ISING_OK;
+}
+
+int ising_tc_accept_table(ising_tc_ctx* c, float out[5])
+{
+    if (!c || !out) TC_RET(tc_fail(ISING_EINVAL, "bad argument"));
+    memcpy(out, c->accept, sizeof(c->accept));
+    return ISING_OK;
+}
+
+static int tc_nn_impl(ising_tc_ctx* c, int is_black, int8_t* out)
+{
+    TC_TRY(cudaSetDevice(c->device));
+    if (!c->scratch) TC_TRY(cudaMalloc(&c->scratch, (size_t)c->n));
+    TC_TRY(cudaMemsetAsync(c->scratch, 0, (size_t)c->n, c->stream));
+    if (int rc = tc_launch_color(c, is_black != 0, 0, c->scratch)) return rc;
+    TC_TRY(cudaMemcpyAsync(out, c->scratch, (size_t)c->n, cudaMemcpyDeviceToHost, c->stream));
+    TC_TRY(cudaStreamSynchronize(c->stream));
+    return ISING_OK;
+}
+int ising_tc_neighbour_sums(ising_tc_ctx* c, int is_black, int8_t* out)
+{
+    if (!c || !out) TC_RET(tc_fail(ISING_EINVAL, "bad argument"));
+    TC_RET(tc_nn_impl(c, is_black, out));
+}
+
+uint64_t ising_tc_launch_count(const ising_tc_ctx* c) { return c ? c->launches : 0; }
+
+}  // extern "C"

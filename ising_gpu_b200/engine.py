@@ -78,6 +78,21 @@ def load_library():
         "ising_accept_table": ([C.c_float, C.POINTER(C.c_float)], None),
         "ising_site_random": ([C.c_uint64, C.c_int32, C.c_int, C.c_int, C.c_uint32, C.c_uint32, C.c_int, u32p], None),
         "ising_launch_count": ([vp], C.c_uint64),
+        "ising_tc_create": ([C.c_int, C.c_int, C.c_uint64, C.c_float, C.c_int, C.POINTER(vp)], C.c_int),
+        "ising_tc_destroy": ([vp], C.c_int),
+        "ising_tc_set_nn_path": ([vp, C.c_int], C.c_int),
+        "ising_tc_init": ([vp], C.c_int),
+        "ising_tc_update": ([vp, C.c_uint64, C.c_int], C.c_int),
+        "ising_tc_update_timed": ([vp, C.c_uint64, C.c_int, C.POINTER(C.c_float)], C.c_int),
+        "ising_tc_sync": ([vp], C.c_int),
+        "ising_tc_sum": ([vp, C.POINTER(C.c_int64)], C.c_int),
+        "ising_tc_export_storage": ([vp, vp], C.c_int),
+        "ising_tc_import_storage": ([vp, vp], C.c_int),
+        "ising_tc_export_true": ([vp, vp], C.c_int),
+        "ising_tc_write_lattice": ([vp, C.c_char_p], C.c_int),
+        "ising_tc_accept_table": ([vp, C.POINTER(C.c_float)], C.c_int),
+        "ising_tc_neighbour_sums": ([vp, C.c_int, vp], C.c_int),
+        "ising_tc_launch_count": ([vp], C.c_uint64),
         "ising_kernel_name": ([vp], C.c_char_p),
     }
     for name, (args, res) in sig.items():
@@ -93,7 +108,11 @@ EXPORTED_SYMBOLS = ("ising_create ising_destroy ising_last_error ising_abi_versi
                     "ising_import_ref_layout ising_export_bits ising_import_bits ising_dump_lattice "
                     "ising_run_from_host ising_row_ptr ising_update_color_part ising_accept_count "
                     "ising_device_count ising_device_info ising_can_access_peer "
-                    "ising_accept_table ising_site_random ising_launch_count ising_kernel_name").split()
+                    "ising_accept_table ising_site_random ising_launch_count ising_kernel_name "
+                    "ising_tc_create ising_tc_destroy ising_tc_set_nn_path ising_tc_init ising_tc_update "
+                    "ising_tc_update_timed ising_tc_sync ising_tc_sum ising_tc_export_storage "
+                    "ising_tc_import_storage ising_tc_export_true ising_tc_write_lattice ising_tc_accept_table "
+                    "ising_tc_neighbour_sums ising_tc_launch_count").split()
 
 
 def accept_count(p, strict=False):

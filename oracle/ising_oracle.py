@@ -54,6 +54,22 @@ def lib():
     L.ora_ghost.restype = C.POINTER(C.c_uint8)
     L.ora_init_count.argtypes = [C.c_int, C.c_longlong, C.c_ulonglong]
     L.ora_init_count.restype = C.c_ulonglong
+    i8p = C.POINTER(C.c_int8)
+    L.tc_create.argtypes = [C.c_int, C.c_int, C.c_ulonglong, C.c_float]
+    L.tc_create.restype = C.c_void_p
+    L.tc_destroy.argtypes = [C.c_void_p]
+    L.tc_set_accept.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
+    L.tc_get_accept.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
+    L.tc_storage.argtypes = [C.c_void_p]
+    L.tc_storage.restype = i8p
+    L.tc_init.argtypes = [C.c_void_p]
+    L.tc_update_color.argtypes = [C.c_void_p, C.c_int, C.c_ulonglong]
+    L.tc_update.argtypes = [C.c_void_p, C.c_ulonglong]
+    L.tc_sum.argtypes = [C.c_void_p]
+    L.tc_sum.restype = C.c_longlong
+    L.tc_export_true.argtypes = [C.c_void_p, i8p]
+    L.tc_neighbour_sums.argtypes = [C.c_void_p, C.c_int, i8p]
+    L.tc_write_lattice.argtypes = [C.c_void_p, C.c_char_p]
     _LIB = L
     return L
 
@@ -176,3 +192,62 @@ def init_count(X, rows, seed=DEFAULT_SEED):
     """(up, down) right after the reference's lattice init, without storing the lattice."""
     up = int(lib().ora_init_count(int(X), int(rows), int(seed)))
     return up, int(X) * int(rows) - up
+
+
+class TensorcoreOracle:
+    """CPU restatement of tensorcore/main.cu (blocked +-1 lattice, its own RNG map)."""
+
+    def __init__(self, nbx, nby, seed=1234, alpha=0.1):
+        self.nbx, self.nby = int(nbx), int(nby)
+        self.nx, self.ny = 256 * self.nbx, 256 * self.nby
+        self._h = lib().tc_create(self.nbx, self.nby, int(seed), C.c_float(float(np.float32(alpha))))
+        self.iter = 0          # iterations done so far (warm-up included), next one uses iter+1
+
+    def close(self):
+        if self._h:
+            lib().tc_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def set_accept(self, table):
+        t = (C.c_float * 5)(*[float(v) for v in table])
+        lib().tc_set_accept(self._h, t)
+
+    def accept(self):
+        t = (C.c_float * 5)()
+        lib().tc_get_accept(self._h, t)
+        return np.array(list(t), dtype=np.float32)
+
+    def init(self):
+        lib().tc_init(self._h)
+        self.iter = 0
+
+    def update(self, n=1):
+        for _ in range(int(n)):
+            self.iter += 1
+            lib().tc_update(self._h, self.iter)
+
+    def update_color(self, is_black, it):
+        lib().tc_update_color(self._h, int(bool(is_black)), int(it))
+
+    def storage(self):
+        p = lib().tc_storage(self._h)
+        return np.ctypeslib.as_array(p, shape=(self.nx * self.ny,))
+
+    def sum(self):
+        return int(lib().tc_sum(self._h))
+
+    def true_lattice(self):
+        out = np.empty((self.ny, self.nx), dtype=np.int8)
+        lib().tc_export_true(self._h, out.ctypes.data_as(C.POINTER(C.c_int8)))
+        return out
+
+    def neighbour_sums(self, is_black):
+        out = np.empty(self.nx * self.ny, dtype=np.int8)
+        lib().tc_neighbour_sums(self._h, int(bool(is_black)), out.ctypes.data_as(C.POINTER(C.c_int8)))
+        return out
+
+    def write_lattice(self, fname):
+        if lib().tc_write_lattice(self._h, os.fsencode(fname)) != 0:
+            raise OSError(fname)
