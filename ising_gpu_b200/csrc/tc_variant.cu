@@ -112,6 +112,221 @@ __global__ void __launch_bounds__(SUBN) tc_update_stencil_kernel(int8_t* __restr
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// Product path: neighbour sums on the 5th-generation tensor cores (tcgen05, INT8 -> INT32 in
+// TMEM), fused with the Metropolis step.
+//
+//   nn[j][i] = sum_k H[j][k] * Kh[k][i]  +  sum_k Kv[j][k] * V[k][i]          (128 x 128 x 128)
+//
+// H = the sub-block holding the left/right neighbours, V = the one holding the up/down
+// neighbours (both int8 +-1 straight from the lattice), Kh/Kv = bidiagonal 0/1 matrices (main
+// diagonal + the sub- or super-diagonal, by the parity (a,b) of the target sub-block): the
+// reference's "lat x K + K^T x lat" (tensorcore/main.cu:547-569) with int8 instead of fp16.
+// Eight tcgen05.mma.kind::i8 (M=128, N=128, K=32) accumulate into one 128-lane x 128-column
+// TMEM tile; H, Kh, Kv are K-major operands, V is used in place as an MN-major B operand (no
+// transposed copy).  All four tiles sit in shared memory in the no-swizzle canonical layout:
+// 8-row x 16-byte core matrices, image(row, byte) below.  The terms that cross the sub-block edge
+// (add_boundaries, main.cu:148-226) are added in the epilogue from the neighbouring blocks.
+// Thread j owns TMEM lane j = row j of the sub-block: tcgen05.ld brings its 128 sums to
+// registers, where the 16 runs of 8 spins are updated with the reference's RNG map.
+// ------------------------------------------------------------------------------------------
+constexpr int TILE_BYTES = SUBN * SUBN;   // 16 KiB per operand tile
+__device__ __forceinline__ int img(int row, int byte)
+{
+    return (row >> 3) * 1024 + (byte >> 4) * 128 + (row & 7) * 16 + (byte & 15);
+}
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo)
+{
+    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) |
+           (1ull << 46);   // version 1 (sm_100), SWIZZLE_NONE, base offset 0
+}
+__host__ __device__ constexpr uint32_t IDESC_I8(int a_mn_major, int b_mn_major)
+{
+    return (2u << 4) /* D = S32 */ | (1u << 7) /* A = INT8 */ | (1u << 10) /* B = INT8 */ |
+           ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) | ((uint32_t)(SUBN >> 3) << 17) |
+           ((uint32_t)(SUBN >> 4) << 24);
+}
+__device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "l"(da), "l"(db), "r"(idesc), "r"(accumulate), "r"(0u)
+        : "memory");
+}
+
+template <bool WRITE_NN>
+__global__ void __launch_bounds__(SUBN, 3) tc_update_mma_kernel(int8_t* __restrict__ lat, int8_t* __restrict__ nn_out,
+                                                               const __grid_constant__ TcParams p)
+{
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint8_t* sH = smem;
+    uint8_t* sV = smem + TILE_BYTES;
+    uint8_t* sKh = smem + 2 * TILE_BYTES;
+    uint8_t* sKv = smem + 3 * TILE_BYTES;
+    __shared__ __align__(8) uint64_t mma_bar;
+    __shared__ uint32_t tmem_base_slot;
+
+    const int sb = blockIdx.x, t = threadIdx.x, warp = t >> 5;
+    int bi, bj;
+    block_of(sb, p.nbx, p.is_black != 0, bi, bj);
+    const int a = bi & 1, b = bj & 1, sx = bi >> 1, sy = bj >> 1;
+    const long long sup = sup_offset(sx, sy, p.nbx);
+    const long long base = sup + sub_offset(a, b);
+    const int8_t* gH = lat + sup + sub_offset(1 - a, b);
+    const int8_t* gV = lat + sup + sub_offset(a, 1 - b);
+    const int di = (a == 0) ? -1 : +1, dj = (b == 0) ? -1 : +1;
+
+    // ---- TMEM allocation (warp 0) and barrier init ------------------------------------------
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_addr(&tmem_base_slot)),
+                     "r"((uint32_t)SUBN)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (t == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr(&mma_bar)));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+
+    // ---- operand tiles: coalesced 16-byte chunks of the two source sub-blocks ----------------
+#pragma unroll
+    for (int u = 0; u < 8; u++) {
+        const int q = t + SUBN * u, row = q >> 3, ch = q & 7;
+        *reinterpret_cast<uint4*>(sH + img(row, 16 * ch)) = *reinterpret_cast<const uint4*>(gH + row * SUBN + 16 * ch);
+        *reinterpret_cast<uint4*>(sV + img(row, 16 * ch)) = *reinterpret_cast<const uint4*>(gV + row * SUBN + 16 * ch);
+    }
+    // bidiagonal matrices, row t of each.  Kh is the B operand stored K-major: row = output column n,
+    // ones at k = n and k = n + di.  Kv is the A operand: row = output row j, ones at k = j and j + dj.
+    {
+        const uint4 z = make_uint4(0, 0, 0, 0);
+#pragma unroll
+        for (int ch = 0; ch < 8; ch++) {
+            *reinterpret_cast<uint4*>(sKh + img(t, 16 * ch)) = z;
+            *reinterpret_cast<uint4*>(sKv + img(t, 16 * ch)) = z;
+        }
+        __syncwarp();
+        sKh[img(t, t)] = 1;
+        sKv[img(t, t)] = 1;
+        if (t + di >= 0 && t + di < SUBN) sKh[img(t, t + di)] = 1;
+        if (t + dj >= 0 && t + dj < SUBN) sKv[img(t, t + dj)] = 1;
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> UMMA (async proxy)
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_d = tmem_base_slot;
+
+    // ---- 8 MMAs issued by one thread, completion signalled on the mbarrier --------------------
+    if (t == 0) {
+        const uint32_t aH = smem_addr(sH), aV = smem_addr(sV), aKh = smem_addr(sKh), aKv = smem_addr(sKv);
+#pragma unroll
+        for (int s = 0; s < 4; s++)      // H (K-major A) x Kh (K-major B): k-step = 2 core matrices = 256 B
+            umma_i8(tmem_d, umma_desc(aH + 256 * s, 128, 1024), umma_desc(aKh + 256 * s, 128, 1024), IDESC_I8(0, 0), s > 0);
+#pragma unroll
+        for (int s = 0; s < 4; s++)      // Kv (K-major A) x V (MN-major B): k-step = 4 groups of 8 rows = 4096 B
+            umma_i8(tmem_d, umma_desc(aKv + 256 * s, 128, 1024), umma_desc(aV + 4096 * s, 1024, 128), IDESC_I8(0, 1), 1u);
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_addr(&mma_bar))
+                     : "memory");
+    }
+
+    // ---- while the tensor core works: own spins, edge terms ----------------------------------
+    const int j = t;
+    uint4 own[8];
+#pragma unroll
+    for (int ch = 0; ch < 8; ch++) own[ch] = *reinterpret_cast<const uint4*>(lat + base + j * SUBN + 16 * ch);
+    // horizontal edge term: lands on column 0 (a == 0) or 127 (a == 1) of every row
+    const int edge_h = spin_at(lat, p.nbx, p.nby, sx, sy, 1 - a, b, (a == 0) ? -1 : SUBN, j);
+    // vertical edge term: a whole row, only for the first (b == 0) or last (b == 1) row of the block
+    const bool has_edge_v = (b == 0) ? (j == 0) : (j == SUBN - 1);
+    const int8_t* edge_row = nullptr;
+    if (has_edge_v) {
+        const int sy2 = (b == 0) ? (sy == 0 ? p.nby - 1 : sy - 1) : (sy == p.nby - 1 ? 0 : sy + 1);
+        edge_row = lat + sup_offset(sx, sy2, p.nbx) + sub_offset(a, 1 - b) + ((b == 0) ? (SUBN - 1) * SUBN : 0);
+    }
+    (void)di;
+
+    // wait for the MMAs
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "W_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n"
+        "@p bra D_%=;\n"
+        "bra W_%=;\n"
+        "D_%=:\n"
+        "}\n" ::"r"(smem_addr(&mma_bar))
+        : "memory");
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+
+    const int n = j / 64;                       // which of the reference thread's two runs this row is
+    const uint64_t tid0 = (uint64_t)sb * TPS + (uint64_t)(16 * (j % 64));
+#pragma unroll 1
+    for (int g = 0; g < 4; g++) {               // 4 groups of 32 columns
+        uint32_t r[32];
+        const uint32_t taddr = tmem_d + ((uint32_t)(warp * 32) << 16) + (uint32_t)(32 * g);
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+            "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+            "tcgen05.wait::ld.sync.aligned;"
+            : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+              "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+              "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+              "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+            : "r"(taddr)
+            : "memory");
+#pragma unroll
+        for (int cc = 0; cc < 4; cc++) {        // 4 runs of 8 spins per group
+            const int c = 4 * g + cc;
+            int8_t ev[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+            if (has_edge_v) *reinterpret_cast<uint2*>(ev) = *reinterpret_cast<const uint2*>(edge_row + 8 * c);
+            int8_t s[8];
+            {
+                const uint4 w = own[c >> 1];
+                const uint2 h2 = (c & 1) ? make_uint2(w.z, w.w) : make_uint2(w.x, w.y);
+                *reinterpret_cast<uint2*>(s) = h2;
+            }
+            uint32_t o[8];
+            if (!WRITE_NN) {
+                const uint64_t tid = tid0 + (uint64_t)c;
+#pragma unroll
+                for (int h = 0; h < 2; h++) {
+                    const uint64_t ctr = p.call0 + 2 * n + h;
+                    philox4x32_10((uint32_t)ctr, (uint32_t)(ctr >> 32), (uint32_t)tid, (uint32_t)(tid >> 32), p.key0,
+                                  p.key1, o + 4 * h);
+                }
+            }
+#pragma unroll
+            for (int m = 0; m < 8; m++) {
+                const int i = 8 * c + m;
+                int nn = (int)r[8 * cc + m] + ev[m];
+                if (i == ((a == 0) ? 0 : SUBN - 1)) nn += edge_h;
+                if (WRITE_NN) {
+                    s[m] = (int8_t)nn;
+                } else {
+                    const int k = (nn * s[m] + 4) >> 1;
+                    const bool flip = p.always[k] || (!p.never[k] && o[m] <= p.thr[k]);
+                    if (flip) s[m] = (int8_t)-s[m];
+                }
+            }
+            int8_t* dst = (WRITE_NN ? nn_out : lat) + base + j * SUBN + 8 * c;
+            *reinterpret_cast<uint2*>(dst) = *reinterpret_cast<uint2*>(s);
+        }
+    }
+
+    // ---- release TMEM -------------------------------------------------------------------------
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"((uint32_t)SUBN) : "memory");
+}
+
 // init_spins: element t <- first output of Philox(subsequence t, offset 0); uniform < 0.5 -> -1
 __global__ void __launch_bounds__(256) tc_init_kernel(int8_t* __restrict__ lat, long long n, uint32_t key0, uint32_t key1,
                                                      uint32_t thr_half)
@@ -166,7 +381,7 @@ int tc_fail(int code, const char* fmt, ...)
 extern "C" void ising_internal_set_error(const char* msg);
 
 struct ising_tc_ctx {
-    int nbx = 0, nby = 0, device = 0, nn_path = ISING_TC_NN_STENCIL;
+    int nbx = 0, nby = 0, device = 0, nn_path = ISING_TC_NN_MMA;
     long long n = 0;
     uint64_t seed = 0;
     float alpha = 0, accept[5];
@@ -227,8 +442,20 @@ static int tc_launch_color(ising_tc_ctx* c, bool black, uint64_t iter, int8_t* n
     p.is_black = black ? 1 : 0;
     p.call0 = (2ull * iter + (black ? 0 : 1)) * 4ull;   // offset (2*iter [+1])*16 draws, main.cu:269/:294
     const int ctas = 2 * c->nbx * c->nby;
-    if (nn_out) tc_update_stencil_kernel<true><<<ctas, SUBN, 0, c->stream>>>(c->lat, nn_out, p);
-    else        tc_update_stencil_kernel<false><<<ctas, SUBN, 0, c->stream>>>(c->lat, nullptr, p);
+    if (c->nn_path == ISING_TC_NN_MMA) {
+        const size_t smem = 4 * TILE_BYTES;
+        static bool attr_set = false;
+        if (!attr_set) {
+            TC_TRY(cudaFuncSetAttribute(tc_update_mma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            TC_TRY(cudaFuncSetAttribute(tc_update_mma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            attr_set = true;
+        }
+        if (nn_out) tc_update_mma_kernel<true><<<ctas, SUBN, smem, c->stream>>>(c->lat, nn_out, p);
+        else        tc_update_mma_kernel<false><<<ctas, SUBN, smem, c->stream>>>(c->lat, nullptr, p);
+    } else {
+        if (nn_out) tc_update_stencil_kernel<true><<<ctas, SUBN, 0, c->stream>>>(c->lat, nn_out, p);
+        else        tc_update_stencil_kernel<false><<<ctas, SUBN, 0, c->stream>>>(c->lat, nullptr, p);
+    }
     TC_TRY(cudaGetLastError());
     c->launches++;
     return ISING_OK;
