@@ -73,17 +73,19 @@ struct StepTables {
     uint32_t k0[7], k1[7];         // keys of rounds 4..10
 };
 
-inline StepTables make_step_tables(uint64_t seed, uint64_t step /* 2*it + colour */)
+// Tables for the 16 consecutive Philox counters base .. base+15 (the low counter word must not
+// carry inside the group: base is a multiple of 16 for the optimized/ map, of 4 -- with 4 calls
+// used -- for the tensorcore/ map).  Subsequence (tid) must be below 2^32.
+inline StepTables make_step_tables_at(uint64_t seed, uint64_t base)
 {
     StepTables t;
     uint32_t k0[10], k1[10];
     k0[0] = (uint32_t)seed; k1[0] = (uint32_t)(seed >> 32);
     for (int r = 1; r < 10; r++) { k0[r] = k0[r - 1] + PHILOX_W0; k1[r] = k1[r - 1] + PHILOX_W1; }
-    const uint64_t base = 16ull * step;   // curand_init offset 64*step draws = 16*step calls
     t.x1 = (uint32_t)(base >> 32) ^ k0[0];
     t.k1r3 = k1[2];
     for (int cl = 0; cl < CALLS_PER_TID; cl++) {
-        const uint32_t c0 = (uint32_t)(base + cl);          // never carries: base is a multiple of 16
+        const uint32_t c0 = (uint32_t)(base + cl);
         uint32_t hi0, lo0, hi1p, lo1p;
         mulhilo(PHILOX_M0, c0, hi0, lo0);
         const uint32_t c2p = hi0 ^ 0u /* tid_hi */ ^ k1[0];
@@ -94,6 +96,12 @@ inline StepTables make_step_tables(uint64_t seed, uint64_t step /* 2*it + colour
     }
     for (int r = 0; r < 7; r++) { t.k0[r] = k0[3 + r]; t.k1[r] = k1[3 + r]; }
     return t;
+}
+
+// optimized/ map: curand_init offset 64*step draws = 16*step calls
+inline StepTables make_step_tables(uint64_t seed, uint64_t step /* 2*it + colour */)
+{
+    return make_step_tables_at(seed, 16ull * step);
 }
 
 // Constant-per-thread part (depends on tid and, through x1, on the step).

@@ -42,6 +42,8 @@ struct TcParams {
     uint32_t always[5];      // ... or always[k] (all ones), and never if never[k]
     uint32_t never[5];
     int is_black;
+    int fast;                // v < 0 always flips, v = 0, 2, 4 have thresholds (every alpha > ~0.16)
+    StepTables st;           // folded Philox schedule of the 4 calls of this colour step
 };
 
 __host__ __device__ __forceinline__ long long sup_offset(long long i, long long j, long long nbx)
@@ -160,9 +162,11 @@ __device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t da, uint64_t d
         : "memory");
 }
 
-template <bool WRITE_NN>
-__global__ void __launch_bounds__(SUBN, 3) tc_update_mma_kernel(int8_t* __restrict__ lat, int8_t* __restrict__ nn_out,
-                                                               const __grid_constant__ TcParams p)
+constexpr int MMA_THREADS = 256;   // warps w and w+4 share TMEM lanes 32(w%4).., split the 128 columns
+
+template <bool WRITE_NN, bool FAST>
+__global__ void __launch_bounds__(MMA_THREADS, 3) tc_update_mma_kernel(int8_t* __restrict__ lat, int8_t* __restrict__ nn_out,
+                                                                      const __grid_constant__ TcParams p)
 {
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t* sH = smem;
@@ -171,8 +175,9 @@ __global__ void __launch_bounds__(SUBN, 3) tc_update_mma_kernel(int8_t* __restri
     uint8_t* sKv = smem + 3 * TILE_BYTES;
     __shared__ __align__(8) uint64_t mma_bar;
     __shared__ uint32_t tmem_base_slot;
+    __shared__ uint32_t lut[8];   // thresholds by (v+4)/2; read as lut[(v+4)/2] = byte offset 2*v + 8
 
-    const int sb = blockIdx.x, t = threadIdx.x, warp = t >> 5;
+    const int sb = blockIdx.x, t = threadIdx.x, warp = t >> 5, lane = t & 31;
     int bi, bj;
     block_of(sb, p.nbx, p.is_black != 0, bi, bj);
     const int a = bi & 1, b = bj & 1, sx = bi >> 1, sy = bj >> 1;
@@ -193,28 +198,27 @@ __global__ void __launch_bounds__(SUBN, 3) tc_update_mma_kernel(int8_t* __restri
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr(&mma_bar)));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    if (t < 5) lut[t] = p.always[t] ? 0xffffffffu : p.thr[t];
 
     // ---- operand tiles: coalesced 16-byte chunks of the two source sub-blocks ----------------
 #pragma unroll
-    for (int u = 0; u < 8; u++) {
-        const int q = t + SUBN * u, row = q >> 3, ch = q & 7;
+    for (int u = 0; u < 4; u++) {
+        const int q = t + MMA_THREADS * u, row = q >> 3, ch = q & 7;
         *reinterpret_cast<uint4*>(sH + img(row, 16 * ch)) = *reinterpret_cast<const uint4*>(gH + row * SUBN + 16 * ch);
         *reinterpret_cast<uint4*>(sV + img(row, 16 * ch)) = *reinterpret_cast<const uint4*>(gV + row * SUBN + 16 * ch);
     }
-    // bidiagonal matrices, row t of each.  Kh is the B operand stored K-major: row = output column n,
-    // ones at k = n and k = n + di.  Kv is the A operand: row = output row j, ones at k = j and j + dj.
+    // bidiagonal matrices: threads 0..127 write row t of Kh, threads 128..255 row t-128 of Kv.
+    // Kh is the B operand stored K-major: row = output column n, ones at k = n and k = n + di.
+    // Kv is the A operand: row = output row j, ones at k = j and k = j + dj.
     {
+        uint8_t* K = (t < SUBN) ? sKh : sKv;
+        const int row = t & (SUBN - 1), d = (t < SUBN) ? di : dj;
         const uint4 z = make_uint4(0, 0, 0, 0);
 #pragma unroll
-        for (int ch = 0; ch < 8; ch++) {
-            *reinterpret_cast<uint4*>(sKh + img(t, 16 * ch)) = z;
-            *reinterpret_cast<uint4*>(sKv + img(t, 16 * ch)) = z;
-        }
+        for (int ch = 0; ch < 8; ch++) *reinterpret_cast<uint4*>(K + img(row, 16 * ch)) = z;
         __syncwarp();
-        sKh[img(t, t)] = 1;
-        sKv[img(t, t)] = 1;
-        if (t + di >= 0 && t + di < SUBN) sKh[img(t, t + di)] = 1;
-        if (t + dj >= 0 && t + dj < SUBN) sKv[img(t, t + dj)] = 1;
+        K[img(row, row)] = 1;
+        if (row + d >= 0 && row + d < SUBN) K[img(row, row + d)] = 1;
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> UMMA (async proxy)
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -236,12 +240,15 @@ __global__ void __launch_bounds__(SUBN, 3) tc_update_mma_kernel(int8_t* __restri
     }
 
     // ---- while the tensor core works: own spins, edge terms ----------------------------------
-    const int j = t;
-    uint4 own[8];
+    const int j = 32 * (warp & 3) + lane;        // row = TMEM lane
+    const int half = warp >> 2;                  // columns 64*half .. 64*half+63
+    uint4 own[4];
 #pragma unroll
-    for (int ch = 0; ch < 8; ch++) own[ch] = *reinterpret_cast<const uint4*>(lat + base + j * SUBN + 16 * ch);
+    for (int ch = 0; ch < 4; ch++) own[ch] = *reinterpret_cast<const uint4*>(lat + base + j * SUBN + 64 * half + 16 * ch);
     // horizontal edge term: lands on column 0 (a == 0) or 127 (a == 1) of every row
-    const int edge_h = spin_at(lat, p.nbx, p.nby, sx, sy, 1 - a, b, (a == 0) ? -1 : SUBN, j);
+    const int edge_col = (a == 0) ? 0 : SUBN - 1;
+    int edge_h = 0;
+    if ((edge_col >> 6) == half) edge_h = spin_at(lat, p.nbx, p.nby, sx, sy, 1 - a, b, (a == 0) ? -1 : SUBN, j);
     // vertical edge term: a whole row, only for the first (b == 0) or last (b == 1) row of the block
     const bool has_edge_v = (b == 0) ? (j == 0) : (j == SUBN - 1);
     const int8_t* edge_row = nullptr;
@@ -249,7 +256,9 @@ __global__ void __launch_bounds__(SUBN, 3) tc_update_mma_kernel(int8_t* __restri
         const int sy2 = (b == 0) ? (sy == 0 ? p.nby - 1 : sy - 1) : (sy == p.nby - 1 ? 0 : sy + 1);
         edge_row = lat + sup_offset(sx, sy2, p.nbx) + sub_offset(a, 1 - b) + ((b == 0) ? (SUBN - 1) * SUBN : 0);
     }
-    (void)di;
+    const int n = j >> 6;                        // which of the reference thread's two runs this row is
+    const uint32_t tid0 = (uint32_t)sb * TPS + (uint32_t)(16 * (j & 63));
+    const uint32_t lut_base = smem_addr(lut) + 8;
 
     // wait for the MMAs
     asm volatile(
@@ -264,12 +273,11 @@ __global__ void __launch_bounds__(SUBN, 3) tc_update_mma_kernel(int8_t* __restri
         : "memory");
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 
-    const int n = j / 64;                       // which of the reference thread's two runs this row is
-    const uint64_t tid0 = (uint64_t)sb * TPS + (uint64_t)(16 * (j % 64));
-#pragma unroll 1
-    for (int g = 0; g < 4; g++) {               // 4 groups of 32 columns
+#pragma unroll
+    for (int g = 0; g < 2; g++) {               // 2 groups of 32 columns per thread
         uint32_t r[32];
-        const uint32_t taddr = tmem_d + ((uint32_t)(warp * 32) << 16) + (uint32_t)(32 * g);
+        const int col0 = 64 * half + 32 * g;
+        const uint32_t taddr = tmem_d + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)col0;
         asm volatile(
             "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
             "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
@@ -281,42 +289,60 @@ __global__ void __launch_bounds__(SUBN, 3) tc_update_mma_kernel(int8_t* __restri
               "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
             : "r"(taddr)
             : "memory");
+        // terms from across the sub-block edge (add_boundaries)
+        if (col0 == 0 && edge_col == 0) r[0] += (uint32_t)edge_h;
+        if (col0 == SUBN - 32 && edge_col == SUBN - 1) r[31] += (uint32_t)edge_h;
+        if (has_edge_v) {
+#pragma unroll
+            for (int q = 0; q < 32; q++) r[q] += (uint32_t)(int)edge_row[col0 + q];
+        }
 #pragma unroll
         for (int cc = 0; cc < 4; cc++) {        // 4 runs of 8 spins per group
-            const int c = 4 * g + cc;
-            int8_t ev[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-            if (has_edge_v) *reinterpret_cast<uint2*>(ev) = *reinterpret_cast<const uint2*>(edge_row + 8 * c);
-            int8_t s[8];
-            {
-                const uint4 w = own[c >> 1];
-                const uint2 h2 = (c & 1) ? make_uint2(w.z, w.w) : make_uint2(w.x, w.y);
-                *reinterpret_cast<uint2*>(s) = h2;
-            }
-            uint32_t o[8];
-            if (!WRITE_NN) {
-                const uint64_t tid = tid0 + (uint64_t)c;
+            const int c = (col0 >> 3) + cc;     // run index inside the row, 0..15
+            const uint4 w4 = own[2 * g + (cc >> 1)];
+            uint32_t w[2] = {(cc & 1) ? w4.z : w4.x, (cc & 1) ? w4.w : w4.y};   // 8 own spins, one per byte
+            if (WRITE_NN) {
+#pragma unroll
+                for (int h = 0; h < 2; h++)
+                    w[h] = (r[8 * cc + 4 * h] & 0xffu) | ((r[8 * cc + 4 * h + 1] & 0xffu) << 8) |
+                           ((r[8 * cc + 4 * h + 2] & 0xffu) << 16) | ((r[8 * cc + 4 * h + 3] & 0xffu) << 24);
+            } else if (FAST) {
+                // one reference thread id per run: fold its constants, then 2 calls of 4 outputs
+                const ThreadConsts tc = make_thread_consts(tid0 + (uint32_t)c, p.st.x1, p.st.k1r3);
 #pragma unroll
                 for (int h = 0; h < 2; h++) {
-                    const uint64_t ctr = p.call0 + 2 * n + h;
-                    philox4x32_10((uint32_t)ctr, (uint32_t)(ctr >> 32), (uint32_t)tid, (uint32_t)(tid >> 32), p.key0,
-                                  p.key1, o + 4 * h);
-                }
-            }
+                    uint32_t o[4];
+                    const int cl = 2 * n + h;   // n is warp-uniform (rows 0..63 / 64..127)
+                    if (n == 0) philox_fast(tc, p.st.a[h], p.st.b[h], p.st.d[h], p.st.k0, p.st.k1, o);
+                    else        philox_fast(tc, p.st.a[2 + h], p.st.b[2 + h], p.st.d[2 + h], p.st.k0, p.st.k1, o);
+                    (void)cl;
+                    uint32_t flipmask = 0;
 #pragma unroll
-            for (int m = 0; m < 8; m++) {
-                const int i = 8 * c + m;
-                int nn = (int)r[8 * cc + m] + ev[m];
-                if (i == ((a == 0) ? 0 : SUBN - 1)) nn += edge_h;
-                if (WRITE_NN) {
-                    s[m] = (int8_t)nn;
-                } else {
-                    const int k = (nn * s[m] + 4) >> 1;
-                    const bool flip = p.always[k] || (!p.never[k] && o[m] <= p.thr[k]);
-                    if (flip) s[m] = (int8_t)-s[m];
+                    for (int m = 0; m < 4; m++) {
+                        const int s = (int)(int8_t)(w[h] >> (8 * m));          // +-1
+                        const int v2 = (int)r[8 * cc + 4 * h + m] * (2 * s);   // 2*nn*s = byte offset into lut
+                        uint32_t thr;
+                        asm("ld.shared.u32 %0, [%1];" : "=r"(thr) : "r"(lut_base + (uint32_t)v2));
+                        if (o[m] <= thr) flipmask |= 0xFEu << (8 * m);          // +1 (0x01) <-> -1 (0xFF)
+                    }
+                    w[h] ^= flipmask;
+                }
+            } else {
+#pragma unroll
+                for (int h = 0; h < 2; h++) {
+                    uint32_t o[4];
+                    const uint64_t ctr = p.call0 + 2 * n + h;
+                    philox4x32_10((uint32_t)ctr, (uint32_t)(ctr >> 32), tid0 + (uint32_t)c, 0u, p.key0, p.key1, o);
+#pragma unroll
+                    for (int m = 0; m < 4; m++) {
+                        const int s = (int)(int8_t)(w[h] >> (8 * m));
+                        const int k = ((int)r[8 * cc + 4 * h + m] * s + 4) >> 1;
+                        if (p.always[k] || (!p.never[k] && o[m] <= p.thr[k])) w[h] ^= 0xFEu << (8 * m);
+                    }
                 }
             }
             int8_t* dst = (WRITE_NN ? nn_out : lat) + base + j * SUBN + 8 * c;
-            *reinterpret_cast<uint2*>(dst) = *reinterpret_cast<uint2*>(s);
+            *reinterpret_cast<uint2*>(dst) = make_uint2(w[0], w[1]);
         }
     }
 
@@ -432,6 +458,8 @@ static int tc_create_impl(int nbx, int nby, uint64_t seed, float alpha, int devi
         c->base.never[k] = (n == 0) ? 0xffffffffu : 0u;
         c->base.thr[k] = (n == 0) ? 0u : (uint32_t)(n - 1);
     }
+    // fast shape: v = -4, -2 always flip; v = 0, 2, 4 are plain thresholds (or "always")
+    c->base.fast = (c->base.always[0] && c->base.always[1] && !c->base.never[2] && !c->base.never[3] && !c->base.never[4]) ? 1 : 0;
     *out = c;
     return ISING_OK;
 }
@@ -446,12 +474,15 @@ static int tc_launch_color(ising_tc_ctx* c, bool black, uint64_t iter, int8_t* n
         const size_t smem = 4 * TILE_BYTES;
         static bool attr_set = false;
         if (!attr_set) {
-            TC_TRY(cudaFuncSetAttribute(tc_update_mma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            TC_TRY(cudaFuncSetAttribute(tc_update_mma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            TC_TRY(cudaFuncSetAttribute(tc_update_mma_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            TC_TRY(cudaFuncSetAttribute(tc_update_mma_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            TC_TRY(cudaFuncSetAttribute(tc_update_mma_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             attr_set = true;
         }
-        if (nn_out) tc_update_mma_kernel<true><<<ctas, SUBN, smem, c->stream>>>(c->lat, nn_out, p);
-        else        tc_update_mma_kernel<false><<<ctas, SUBN, smem, c->stream>>>(c->lat, nullptr, p);
+        p.st = make_step_tables_at(c->seed, p.call0);
+        if (nn_out)       tc_update_mma_kernel<true, false><<<ctas, MMA_THREADS, smem, c->stream>>>(c->lat, nn_out, p);
+        else if (p.fast)  tc_update_mma_kernel<false, true><<<ctas, MMA_THREADS, smem, c->stream>>>(c->lat, nullptr, p);
+        else              tc_update_mma_kernel<false, false><<<ctas, MMA_THREADS, smem, c->stream>>>(c->lat, nullptr, p);
     } else {
         if (nn_out) tc_update_stencil_kernel<true><<<ctas, SUBN, 0, c->stream>>>(c->lat, nn_out, p);
         else        tc_update_stencil_kernel<false><<<ctas, SUBN, 0, c->stream>>>(c->lat, nullptr, p);
