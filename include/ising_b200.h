@@ -69,12 +69,15 @@ typedef struct ising_cfg {
     int32_t slab_first;   /* global slab index of this context's device 0                      */
     int32_t slab_count;   /* slabs in the global lattice (0 -> ndev)                            */
     int32_t flags;        /* ISING_F_* */
-    int32_t reserved[5];
+    float j_prob;         /* -J: probability that a bond is antiferromagnetic (with ISING_F_BONDS) */
+    int32_t reserved[4];
 } ising_cfg;
 
 enum {
-    ISING_F_NO_PEER_COPY = 1 /* multi-slab context whose ghost rows are filled by the caller
-                                (NCCL send/recv or IPC stores), not by the library           */
+    ISING_F_NO_PEER_COPY = 1, /* multi-slab context whose ghost rows are filled by the caller
+                                 (NCCL send/recv or IPC stores), not by the library           */
+    ISING_F_BONDS = 2         /* -J: random +-J bonds, hamiltInitB_k/hamiltInitW_k (main.cu:153-331,
+                                 applied in the update as main.cu:575-618)                    */
 };
 
 /* ---- lifetime --------------------------------------------------------------------------
@@ -117,6 +120,17 @@ int ising_count_spins(ising_ctx* ctx, uint64_t* up, uint64_t* down);
 /* Sum over nearest-neighbour bonds of s_i*s_j (s = +-1) for the context's slabs; energy per
  * site = -bond_sum / (rows*X).  (The reference exposes this only via -c, main.cu:1129-1135.) */
 int ising_bond_sum(ising_ctx* ctx, int64_t* bond_sum);
+
+/* Two-point correlation (-c; computeCorr + getCorr2D_k / getCorr2DRepl_k, main.cu:870-1138):
+ * out[j-1], j = 1..ncorr (the reference uses 128), = sum over all sites of (+1 if equal else -1)
+ * for the site j columns to the right and the site j rows below, periodic inside the
+ * (sub-)lattice, divided by 2*X*rows -- the numbers the reference writes to its corr_ file.
+ * Single-process contexts only (any ndev). */
+int ising_correlation(ising_ctx* ctx, int ncorr, double* out);
+/* +-J bond nibbles of one device's slab in the reference's 4-bit words (bit 3 up, 2 down, 1 left,
+ * 0 right): `random` = the buffer hamiltInitB_k fills (used by the WHITE update, main.cu:1796),
+ * `mirror` = the one hamiltInitW_k derives (used by the BLACK update, main.cu:1775).  For tests. */
+int ising_export_bonds_ref_layout(ising_ctx* ctx, int dev, uint64_t* random, uint64_t* mirror);
 
 /* ---- lattice transfer ------------------------------------------------------------------*/
 /* Reference storage format of one device's slab (main.cu:1160-1175): Y*X/32 uint64 words per

@@ -229,10 +229,6 @@ int main(int argc, char** argv)
     std::vector<unsigned long long> printExpSteps;
     if (printExp) printExpSteps = exp_series((unsigned long long)nsteps);
 
-    if (corrOut || useGenHamilt) {
-        fprintf(stderr, "error: options -c and -J are not part of this build yet (see DESIGN.md, scope)\n");
-        exit(EXIT_FAILURE);
-    }
 
     printf("\nUsing GPUs:\n");
     for (int i = 0; i < ndev; i++) {
@@ -290,7 +286,8 @@ int main(int argc, char** argv)
     printf("\ttemp: %f (%f*T_crit)\n", temp, temp / ISING_CRIT_TEMP);
     if (!tempUpdFreq) printf("\ttemp update not set\n");
     else printf("\ttemp update: %f / %d iterations\n", tempUpdStep, tempUpdFreq);
-    printf("\tnot using Hamiltonian buffer\n");
+    if (useGenHamilt) printf("\tusing Hamiltonian buffer, setting links to -1 with prob %G\n", hamiltPerc1);
+    else printf("\tnot using Hamiltonian buffer\n");
     printf("\n");
     if (useSubLatt) {
         printf("\tusing sub-lattices:\n");
@@ -310,6 +307,7 @@ int main(int argc, char** argv)
     memset(&cfg, 0, sizeof(cfg));
     cfg.X = X; cfg.Y = Y; cfg.ndev = ndev; cfg.first_device = 0; cfg.seed = seed; cfg.temp = temp;
     cfg.xsl = useSubLatt ? XSL : 0; cfg.ysl = useSubLatt ? YSL : 0;
+    if (useGenHamilt) { cfg.flags |= ISING_F_BONDS; cfg.j_prob = hamiltPerc1; }
     ising_ctx* ctx = nullptr;
     ISING_CALL(ising_create(&cfg, &ctx));
 
@@ -321,6 +319,21 @@ int main(int argc, char** argv)
            (unsigned long long)cntNeg);
     ISING_CALL(ising_sync(ctx));
 
+    // -c: one line per measure appended to corr_{Y}x{X}_T_{TEMP}_{SEED} (main.cu:1661, :1129-1135);
+    // the file name keeps the temperature of the start of the run, as in the reference
+    char cname[256];
+    snprintf(cname, sizeof(cname), "corr_%dx%d_T_%f_%llu", Y, X, temp, seed);
+    if (corrOut) remove(cname);
+    auto corr = [&](int it) {
+        double c[MAX_CORR_LEN];
+        ISING_CALL(ising_correlation(ctx, MAX_CORR_LEN, c));
+        FILE* fp = fopen(cname, "a");
+        if (!fp) { fprintf(stderr, "cannot open %s\n", cname); exit(EXIT_FAILURE); }
+        fprintf(fp, "%10d", it);
+        for (int i = 0; i < MAX_CORR_LEN; i++) fprintf(fp, " % -12G", c[i]);
+        fprintf(fp, "\n");
+        fclose(fp);
+    };
     auto dump = [&](int it) {
         char fname[256];
         snprintf(fname, sizeof(fname), "lattice_%dx%d_T_%f_IT_%08d_", Y, X, temp, it);   // main.cu:1816
@@ -341,6 +354,7 @@ int main(int argc, char** argv)
             const double magn = fabs((double)cntPos - (double)cntNeg) / (double)nspins;
             printf("        magnetization: %9.6lf, up_s: %12llu, dw_s: %12llu (iter: %8d)\n", magn,
                    (unsigned long long)cntPos, (unsigned long long)cntNeg, j + 1);
+            if (corrOut) corr(j + 1);
             if (dumpOut) dump(j + 1);
             if (tgtMagn != -1.0 && fabs(magn - tgtMagn) < TGT_MAGN_MAX_DIFF) stop = true;
         }
@@ -350,6 +364,7 @@ int main(int argc, char** argv)
             const double magn = fabs((double)cntPos - (double)cntNeg) / (double)nspins;
             printf("        magnetization: %9.6lf (^2: %9.6lf), up_s: %12llu, dw_s: %12llu (iter: %8d)\n", magn,
                    magn * magn, (unsigned long long)cntPos, (unsigned long long)cntNeg, j + 1);
+            if (corrOut) corr(j + 1);
             if (dumpOut) dump(j + 1);
             if (tgtMagn != -1.0 && fabs(magn - tgtMagn) < TGT_MAGN_MAX_DIFF) stop = true;
         }

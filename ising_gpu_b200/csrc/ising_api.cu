@@ -60,6 +60,9 @@ struct DevState {
     bool own_stream = true;
     uint32_t* plane[2] = {nullptr, nullptr};   // (Y+2) x pitch words; row 0 / Y+1 are ghost rows
     CUtensorMap map_tile[2], map_row[2], map_side[2];
+    uint32_t* bond_random = nullptr;           // 4 planes x (Y+2) x pitch (hamiltInitB_k), with edge rows
+    uint32_t* bond_mirror = nullptr;           // 4 planes x Y x pitch (hamiltInitW_k)
+    unsigned long long* d_corr = nullptr;
     unsigned long long* d_counts = nullptr;    // [0] up-count, [1] unequal bonds
     cudaEvent_t ev_color = nullptr;            // kernel + halo pushes of the last colour issued
     cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;
@@ -71,6 +74,7 @@ struct ising_ctx {
     ising_cfg cfg;
     int pitch = 0;        // 32-site words per colour row = X/64
     int slab_count = 1;
+    bool bonds = false;
     bool peer_halo = false;   // library copies boundary rows between its own devices
     bool ghost_rows = false;  // vertical neighbours of the slab edge come from ghost rows
     int yperiod = 0, xperiod = 0;
@@ -133,6 +137,7 @@ UpdateParams base_params(const ising_ctx* c, int dev, int color, int it)
     p.yperiod = c->yperiod;
     p.xperiod = c->xperiod;
     p.color = color;
+    p.bond_rows = (color == 0) ? c->cfg.Y : c->cfg.Y + 2;   // black uses the mirror planes, white the random ones
     return p;
 }
 
@@ -151,7 +156,12 @@ int launch_part(ising_ctx* c, int dev, int color, int it, int part, cudaStream_t
         if (gy <= 0) return ISING_OK;
     }
     CU_TRY(cudaSetDevice(d.device));
-    launch_update(d.map_tile[src], d.map_row[src], d.map_side[src], local_row(c, d, color, 0), p, tiles_x, gy, stream);
+    // the reference hands the BLACK update the hamiltInitW_k buffer and the WHITE update the
+    // hamiltInitB_k one (main.cu:1775, :1796)
+    const uint32_t* bonds = nullptr;
+    if (c->bonds) bonds = (color == 0) ? d.bond_mirror : d.bond_random + c->pitch;   // local row 0
+    launch_update(d.map_tile[src], d.map_row[src], d.map_side[src], local_row(c, d, color, 0), bonds, p, tiles_x, gy,
+                  stream);
     CU_TRY(cudaGetLastError());
     c->launches++;
     return ISING_OK;
@@ -268,11 +278,11 @@ int ising_create(const ising_cfg* cfg, ising_ctx** out)
     auto cleanup = [&](int rc) { ising_destroy(c); return rc; };
     for (int i = 0; i < cfg->ndev; i++) c->dev[i].device = cfg->first_device + i;
 
-    if (c->peer_halo) {   // main.cu:1513-1536
+    c->bonds = (cfg->flags & ISING_F_BONDS) != 0;
+    if (cfg->ndev > 1) {   // all pairs, as main.cu:1513-1536 (halo ring + correlation reads)
         for (int i = 0; i < cfg->ndev; i++) {
             if (cudaSetDevice(c->dev[i].device) != cudaSuccess) return cleanup(fail(ISING_ECUDA, "cudaSetDevice failed"));
-            for (int k = -1; k <= 1; k += 2) {
-                const int j = (i + k + cfg->ndev) % cfg->ndev;
+            for (int j = 0; j < cfg->ndev; j++) {
                 if (j == i) continue;
                 int ok = 0;
                 cudaDeviceCanAccessPeer(&ok, c->dev[i].device, c->dev[j].device);
@@ -303,6 +313,11 @@ int ising_create(const ising_cfg* cfg, ising_ctx** out)
             if ((rc = make_map(&d.map_side[col], d.plane[col], c->pitch, cfg->Y + 2, SIDE_W, TH))) return cleanup(rc);
         }
         if ((e = cudaMalloc(&d.d_counts, 2 * sizeof(unsigned long long))) != cudaSuccess) return cleanup(fail(ISING_ENOMEM, "%s", cudaGetErrorString(e)));
+        if (c->bonds) {
+            if ((e = cudaMalloc(&d.bond_random, 4 * plane_bytes)) != cudaSuccess ||
+                (e = cudaMalloc(&d.bond_mirror, 4 * (size_t)cfg->Y * c->pitch * 4)) != cudaSuccess)
+                return cleanup(fail(ISING_ENOMEM, "bond planes: %s", cudaGetErrorString(e)));
+        }
         if ((e = cudaEventCreateWithFlags(&d.ev_color, cudaEventDisableTiming)) != cudaSuccess ||
             (e = cudaEventCreate(&d.ev_t0)) != cudaSuccess || (e = cudaEventCreate(&d.ev_t1)) != cudaSuccess)
             return cleanup(fail(ISING_ECUDA, "event: %s", cudaGetErrorString(e)));
@@ -320,6 +335,9 @@ int ising_destroy(ising_ctx* c)
         if (d.stream) cudaStreamSynchronize(d.stream);
         for (int col = 0; col < 2; col++) if (d.plane[col]) cudaFree(d.plane[col]);
         if (d.d_counts) cudaFree(d.d_counts);
+        if (d.bond_random) cudaFree(d.bond_random);
+        if (d.bond_mirror) cudaFree(d.bond_mirror);
+        if (d.d_corr) cudaFree(d.d_corr);
         if (d.ev_color) cudaEventDestroy(d.ev_color);
         if (d.ev_t0) cudaEventDestroy(d.ev_t0);
         if (d.ev_t1) cudaEventDestroy(d.ev_t1);
@@ -368,9 +386,99 @@ int ising_init_lattice(ising_ctx* c)
             c->launches++;
         }
     }
+    if (c->bonds) {   // main.cu:1728-1742
+        for (int i = 0; i < (int)c->dev.size(); i++) {
+            DevState& d = c->dev[i];
+            CU_TRY(cudaSetDevice(d.device));
+            BondParams b{};
+            const uint64_t s1 = c->cfg.seed + 1ull;
+            b.key0 = (uint32_t)s1; b.key1 = (uint32_t)(s1 >> 32);
+            const uint64_t n = accept_count(c->cfg.j_prob, true);   // uniform < prob
+            b.always = (n == (1ull << 32)); b.never = (n == 0); b.thr = n ? (uint32_t)(n - 1) : 0u;
+            b.grid_x = (uint32_t)(c->cfg.X / 2048);
+            b.grow0 = (uint32_t)(c->cfg.slab_first + i) * (uint32_t)c->cfg.Y;
+            b.total_rows = (long long)c->slab_count * c->cfg.Y;
+            b.rows = c->cfg.Y; b.pitch = c->pitch; b.yperiod = c->yperiod; b.xperiod = c->xperiod;
+            launch_bond_init(d.bond_random, d.bond_mirror, b, d.stream);
+            CU_TRY(cudaGetLastError());
+            c->launches += 2;
+        }
+    }
     if (c->peer_halo) {
         if (int rc = push_halo(c, 0)) return rc;
         if (int rc = push_halo(c, 1)) return rc;
+    }
+    return ISING_OK;
+}
+
+int ising_correlation(ising_ctx* c, int ncorr, double* out)
+{
+    if (!c || !out || ncorr < 1 || ncorr > 4096) return fail(ISING_EINVAL, "bad argument");
+    const int n = (int)c->dev.size();
+    if (c->slab_count != n) return fail(ISING_ESTATE, "ising_correlation needs the whole lattice in one context");
+    if (n > MAX_CORR_SLABS) return fail(ISING_ESTATE, "ising_correlation supports up to %d devices", MAX_CORR_SLABS);
+    if (2 * (size_t)c->pitch * 4 > 200 * 1024) return fail(ISING_ESTATE, "X too large for the correlation kernel");
+    if (int rc = ising_sync(c)) return rc;
+    CorrParams p{};
+    for (int i = 0; i < n; i++) { p.black[i] = local_row(c, c->dev[i], 0, 0); p.white[i] = local_row(c, c->dev[i], 1, 0); }
+    p.rows = c->cfg.Y; p.pitch = c->pitch; p.ncorr = ncorr;
+    p.yperiod = (c->cfg.xsl || c->cfg.ysl) ? (long long)(c->cfg.ysl ? c->cfg.ysl : c->cfg.Y) : (long long)n * c->cfg.Y;
+    p.xperiod = c->xperiod;
+    std::vector<unsigned long long> tot(ncorr, 0ull), h(ncorr);
+    for (int i = 0; i < n; i++) {
+        DevState& d = c->dev[i];
+        CU_TRY(cudaSetDevice(d.device));
+        if (!d.d_corr) CU_TRY(cudaMalloc(&d.d_corr, 4096 * sizeof(unsigned long long)));
+        CU_TRY(cudaMemsetAsync(d.d_corr, 0, ncorr * sizeof(unsigned long long), d.stream));
+        p.self = i; p.grow0 = (long long)i * c->cfg.Y;
+        static bool attr = false;
+        (void)attr;
+        launch_corr(p, d.d_corr, d.stream);
+        CU_TRY(cudaGetLastError());
+        c->launches++;
+    }
+    for (int i = 0; i < n; i++) {
+        DevState& d = c->dev[i];
+        CU_TRY(cudaSetDevice(d.device));
+        CU_TRY(cudaMemcpyAsync(h.data(), d.d_corr, ncorr * sizeof(unsigned long long), cudaMemcpyDeviceToHost, d.stream));
+        CU_TRY(cudaStreamSynchronize(d.stream));
+        for (int j = 0; j < ncorr; j++) tot[j] += h[j];
+    }
+    // equal pairs E of 2N pairs (N sites, right + below): sum of +-1 = 2E - 2N, normalised by 2N
+    const double N = (double)n * (double)c->cfg.Y * (double)c->cfg.X;
+    for (int j = 0; j < ncorr; j++) out[j] = (2.0 * (double)tot[j] - 2.0 * N) / (2.0 * N);
+    return ISING_OK;
+}
+
+int ising_export_bonds_ref_layout(ising_ctx* c, int dev, uint64_t* random, uint64_t* mirror)
+{
+    if (!c || dev < 0 || dev >= (int)c->dev.size()) return fail(ISING_EINVAL, "bad device index");
+    if (!c->bonds) return fail(ISING_ESTATE, "context created without ISING_F_BONDS");
+    DevState& d = c->dev[dev];
+    const size_t words = (size_t)c->cfg.Y * c->pitch;
+    std::vector<uint32_t> pl(4 * words);
+    CU_TRY(cudaSetDevice(d.device));
+    CU_TRY(cudaStreamSynchronize(d.stream));
+    for (int which = 0; which < 2; which++) {
+        uint64_t* out = which ? mirror : random;
+        if (!out) continue;
+        for (int k = 0; k < 4; k++) {
+            const uint32_t* src = which ? d.bond_mirror + k * words
+                                        : d.bond_random + k * (size_t)(c->cfg.Y + 2) * c->pitch + c->pitch;
+            CU_TRY(cudaMemcpy(pl.data() + k * words, src, words * 4, cudaMemcpyDeviceToHost));
+        }
+        // plane k: 0 up (bit 3), 1 down (bit 2), 2 left (bit 1), 3 right (bit 0)
+        for (size_t w = 0; w < words; w++)
+            for (int hlf = 0; hlf < 2; hlf++) {
+                uint64_t v = 0;
+                for (int z = 0; z < 16; z++) {
+                    const int b = 16 * hlf + z;
+                    const uint64_t nib = (((pl[0 * words + w] >> b) & 1u) << 3) | (((pl[1 * words + w] >> b) & 1u) << 2) |
+                                         (((pl[2 * words + w] >> b) & 1u) << 1) | ((pl[3 * words + w] >> b) & 1u);
+                    v |= nib << (4 * z);
+                }
+                out[2 * w + hlf] = v;
+            }
     }
     return ISING_OK;
 }

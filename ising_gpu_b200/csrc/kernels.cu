@@ -260,10 +260,11 @@ __device__ __forceinline__ uint32_t flip_mask(uint32_t me, uint32_t up, uint32_t
 #ifndef ISING_MIN_BLOCKS
 #define ISING_MIN_BLOCKS 4
 #endif
-template <bool FAST>
+template <bool FAST, bool BONDS>
 __global__ void __launch_bounds__(UPDATE_THREADS, ISING_MIN_BLOCKS)
 update_color_kernel(const __grid_constant__ CUtensorMap src_tile, const __grid_constant__ CUtensorMap src_row,
                     const __grid_constant__ CUtensorMap src_side, uint32_t* __restrict__ dst /* local row 0 */,
+                    const uint32_t* __restrict__ bonds /* 4 planes: up, down, left, right; local row 0 */,
                     const __grid_constant__ UpdateParams p)
 {
     __shared__ alignas(128) uint32_t sV[(TH + 2) * TW];   // rows: above, 16 centre rows, below
@@ -281,6 +282,16 @@ update_color_kernel(const __grid_constant__ CUtensorMap src_tile, const __grid_c
     uint32_t me[2];
     me[0] = my[0];
     me[1] = my[16];
+    // +-J bonds of the thread's sites (main.cu:575-618): one bit plane per direction
+    uint32_t jb[2][4];
+    if (BONDS) {
+        const size_t plane = (size_t)p.bond_rows * p.pitch, off = (size_t)(y0 + ty) * p.pitch + x0 + tx;
+#pragma unroll
+        for (int d = 0; d < 4; d++) {
+            jb[0][d] = bonds[d * plane + off];
+            jb[1][d] = bonds[d * plane + off + 16];
+        }
+    }
 
     if (threadIdx.x == 0) {
         mbar_init(&bar, 1);
@@ -328,9 +339,9 @@ update_color_kernel(const __grid_constant__ CUtensorMap src_tile, const __grid_c
 #pragma unroll
     for (int j = 0; j < 2; j++) {
         const int w = tx + 16 * j;
-        const uint32_t up = sV[ty * TW + w];
-        const uint32_t ct = sV[(ty + 1) * TW + w];
-        const uint32_t dn = sV[(ty + 2) * TW + w];
+        uint32_t up = sV[ty * TW + w];
+        uint32_t ct = sV[(ty + 1) * TW + w];
+        uint32_t dn = sV[(ty + 2) * TW + w];
         uint32_t sd;
         if (read_back) {
             const uint32_t prev = (w == 0) ? sL[ty * SIDE_W + SIDE_W - 1] : sV[(ty + 1) * TW + w - 1];
@@ -339,18 +350,32 @@ update_color_kernel(const __grid_constant__ CUtensorMap src_tile, const __grid_c
             const uint32_t next = (w == TW - 1) ? sR[ty * SIDE_W] : sV[(ty + 1) * TW + w + 1];
             sd = __funnelshift_r(ct, next, 1);    // (ct >> 1) | (next << 31)
         }
+        if (BONDS) {   // an antiferromagnetic bond flips the neighbour's sign as seen by this site
+            up ^= jb[j][0];
+            dn ^= jb[j][1];
+            if (read_back) { sd ^= jb[j][2]; ct ^= jb[j][3]; }   // sd = left neighbour, ct = right
+            else           { ct ^= jb[j][2]; sd ^= jb[j][3]; }   // ct = left neighbour, sd = right
+        }
         my[16 * j] = me[j] ^ flip_mask<FAST>(me[j], up, dn, ct, sd, rejA[j], rejB[j], p.rule);
     }
 }
 
 void launch_update(const CUtensorMap& src_tile, const CUtensorMap& src_row, const CUtensorMap& src_side,
-                   uint32_t* dst, const UpdateParams& p, int tiles_x, int tiles_y, cudaStream_t stream)
+                   uint32_t* dst, const uint32_t* bonds, const UpdateParams& p, int tiles_x, int tiles_y,
+                   cudaStream_t stream)
 {
     const dim3 grid((unsigned)tiles_x, (unsigned)tiles_y);
-    if (p.rule.fast)
-        update_color_kernel<true><<<grid, UPDATE_THREADS, 0, stream>>>(src_tile, src_row, src_side, dst, p);
-    else
-        update_color_kernel<false><<<grid, UPDATE_THREADS, 0, stream>>>(src_tile, src_row, src_side, dst, p);
+    if (bonds) {
+        if (p.rule.fast)
+            update_color_kernel<true, true><<<grid, UPDATE_THREADS, 0, stream>>>(src_tile, src_row, src_side, dst, bonds, p);
+        else
+            update_color_kernel<false, true><<<grid, UPDATE_THREADS, 0, stream>>>(src_tile, src_row, src_side, dst, bonds, p);
+    } else {
+        if (p.rule.fast)
+            update_color_kernel<true, false><<<grid, UPDATE_THREADS, 0, stream>>>(src_tile, src_row, src_side, dst, nullptr, p);
+        else
+            update_color_kernel<false, false><<<grid, UPDATE_THREADS, 0, stream>>>(src_tile, src_row, src_side, dst, nullptr, p);
+    }
 }
 
 const char* update_kernel_name(int fast)
@@ -460,6 +485,157 @@ void launch_bond_differ(const uint32_t* black, const uint32_t* white, int rows, 
                         uint32_t grow0, unsigned long long* counts, cudaStream_t stream)
 {
     bond_differ_kernel<<<148 * 8, 256, 0, stream>>>(black, white, rows, pitch, yperiod, xperiod, grow0, counts);
+}
+
+// ------------------------------------------------------------------------------------------
+// +-J bonds.  bond_random_kernel = hamiltInitB_k (main.cu:153-212): per reference thread 64 Philox
+// calls of curand_init(seed+1, tid, 0); draw 128*j + 8*z + 2*l + h decides bit l (0 right, 1 left,
+// 2 down, 3 up) of site 16*h + z of word c0 + 16*j; bit set iff uniform < prob.  Rows -1 and Y
+// (the neighbouring slabs' edge rows, recomputed from their global row) are filled too so that
+// bond_mirror_kernel = hamiltInitW_k (main.cu:214-331) needs no communication.
+// Planes: 0 = up, 1 = down, 2 = left, 3 = right, each bond_rows x pitch words.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(UPDATE_THREADS) bond_random_kernel(uint32_t* __restrict__ planes /* alloc row 0 */,
+                                                                   const __grid_constant__ BondParams p)
+{
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    const int x0 = blockIdx.x * TW;
+    const int arow = blockIdx.y * TH + ty;            // allocation row 0 .. Y+1
+    if (arow >= p.rows + 2) return;
+    // global row of allocation row arow (local row arow-1), periodic over the whole lattice
+    const long long g = ((long long)p.grow0 + arow - 1 + p.total_rows) % p.total_rows;
+    const uint32_t tid = ref_tid((uint32_t)g, (uint32_t)(x0 + tx), p.grid_x);
+    const size_t plane = (size_t)(p.rows + 2) * p.pitch;
+#pragma unroll 1
+    for (int j = 0; j < 2; j++) {
+        uint32_t acc[4] = {0, 0, 0, 0};                // by bit l
+#pragma unroll 1
+        for (int z = 0; z < 16; z++) {
+#pragma unroll
+            for (int lh = 0; lh < 2; lh++) {
+                uint32_t o[4];
+                philox4x32_10((uint32_t)(32 * j + 2 * z + lh), 0u, tid, 0u, p.key0, p.key1, o);
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    const int l = 2 * lh + (q >> 1), h = q & 1;
+                    const bool set = p.always ? true : (!p.never && o[q] <= p.thr);
+                    if (set) acc[l] |= 1u << (16 * h + z);
+                }
+            }
+        }
+        const size_t off = (size_t)arow * p.pitch + x0 + tx + 16 * j;
+        planes[0 * plane + off] = acc[3];   // up
+        planes[1 * plane + off] = acc[2];   // down
+        planes[2 * plane + off] = acc[1];   // left
+        planes[3 * plane + off] = acc[0];   // right
+    }
+}
+
+__global__ void __launch_bounds__(256) bond_mirror_kernel(const uint32_t* __restrict__ src /* alloc row 0, rows+2 */,
+                                                         uint32_t* __restrict__ dst /* local row 0, rows */,
+                                                         const __grid_constant__ BondParams p)
+{
+    const size_t n = (size_t)p.rows * p.pitch;
+    const size_t splane = (size_t)(p.rows + 2) * p.pitch, dplane = n;
+    const uint32_t* s0 = src + p.pitch;     // local row 0 of the source planes
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const int r = (int)(i / p.pitch), w = (int)(i % p.pitch);
+        int ru, rd;
+        if (p.yperiod > 0) {
+            ru = (r % p.yperiod == 0) ? r + p.yperiod - 1 : r - 1;
+            rd = ((r + 1) % p.yperiod == 0) ? r + 1 - p.yperiod : r + 1;
+        } else {
+            ru = r - 1; rd = r + 1;
+        }
+        const int wl = (w % p.xperiod == 0) ? w + p.xperiod - 1 : w - 1;
+        const int wr = ((w + 1) % p.xperiod == 0) ? w + 1 - p.xperiod : w + 1;
+        const bool odd = ((p.grow0 + (uint32_t)r) & 1u) != 0;
+        const uint32_t* up_ = s0 + 0 * splane; const uint32_t* dn_ = s0 + 1 * splane;
+        const uint32_t* lf_ = s0 + 2 * splane; const uint32_t* rt_ = s0 + 3 * splane;
+        const ptrdiff_t row = (ptrdiff_t)r * p.pitch;
+        // my up = down bond of the site above, my down = up bond of the site below
+        dst[0 * dplane + i] = dn_[(ptrdiff_t)ru * p.pitch + w];
+        dst[1 * dplane + i] = up_[(ptrdiff_t)rd * p.pitch + w];
+        uint32_t left, right;
+        if (!odd) {   // even rows: left partner is site m of the source, right partner is m+1
+            left = rt_[row + w];
+            right = __funnelshift_r(lf_[row + w], lf_[row + wr], 1);
+        } else {      // odd rows: left partner is m-1, right partner is m
+            left = __funnelshift_l(rt_[row + wl], rt_[row + w], 1);
+            right = lf_[row + w];
+        }
+        dst[2 * dplane + i] = left;
+        dst[3 * dplane + i] = right;
+    }
+}
+
+void launch_bond_init(uint32_t* random_planes, uint32_t* mirror_planes, const BondParams& p, cudaStream_t stream)
+{
+    const dim3 grid((unsigned)(p.pitch / TW), (unsigned)((p.rows + 2 + TH - 1) / TH));
+    bond_random_kernel<<<grid, UPDATE_THREADS, 0, stream>>>(random_planes, p);
+    bond_mirror_kernel<<<148 * 8, 256, 0, stream>>>(random_planes, mirror_planes, p);
+}
+
+// ------------------------------------------------------------------------------------------
+// Two-point correlation (getCorr2D_k / getCorr2DRepl_k, main.cu:870-1070): for every site the
+// site j columns to the right and j rows below, j = 1..ncorr.  In the 1-bit colour planes both
+// are plain XORs: a shift of j = 2d columns pairs black with black and white with white d bits
+// on; j = 2d+1 pairs black m with white m+d+rho and white m with black m+d+1-rho (rho = row
+// parity); j rows below pairs equal colours for even j and swapped colours for odd j at the same
+// bit.  One CTA per row; counts of EQUAL pairs are accumulated, the host turns them into the
+// reference's normalised (+1/-1) sums.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t rot_word(const uint32_t* __restrict__ row, int w, int shift, int period)
+{
+    // word w of `row` rotated left by `shift` sites inside its period-aligned segment:
+    // result bit b = site (32*w + b + shift) of the segment (periodic)
+    const int seg = (w / period) * period, wl = w - seg;
+    const int ws = shift >> 5, bs = shift & 31;
+    const uint32_t lo = row[seg + (wl + ws) % period];
+    const uint32_t hi = row[seg + (wl + ws + 1) % period];
+    return __funnelshift_r(lo, hi, bs);
+}
+
+__global__ void __launch_bounds__(128) corr_kernel(const __grid_constant__ CorrParams p, unsigned long long* __restrict__ equal)
+{
+    extern __shared__ uint32_t sRow[];          // black row, white row
+    uint32_t* sB = sRow;
+    uint32_t* sW = sRow + p.pitch;
+    const int r = blockIdx.x;                     // local row
+    const long long g = (long long)p.grow0 + r;   // global row
+    const int rho = (int)(g & 1);
+    const uint32_t* B = p.black[p.self] + (size_t)r * p.pitch;
+    const uint32_t* W = p.white[p.self] + (size_t)r * p.pitch;
+    for (int w = threadIdx.x; w < p.pitch; w += blockDim.x) { sB[w] = B[w]; sW[w] = W[w]; }
+    __syncthreads();
+    for (int j = 1; j <= p.ncorr; j++) {
+        unsigned long long acc = 0;
+        // row j below, periodic inside the (sub-)lattice
+        const long long base = (g / p.yperiod) * p.yperiod;
+        const long long gj = base + (g - base + j) % p.yperiod;
+        const int slab = (int)(gj / p.rows), rj = (int)(gj % p.rows);
+        const uint32_t* Bj = p.black[slab] + (size_t)rj * p.pitch;
+        const uint32_t* Wj = p.white[slab] + (size_t)rj * p.pitch;
+        const int d = j >> 1;
+        for (int w = threadIdx.x; w < p.pitch; w += blockDim.x) {
+            const uint32_t b = sB[w], wh = sW[w];
+            if (j & 1) {
+                acc += __popc(~(b ^ rot_word(sW, w, d + rho, p.xperiod))) + __popc(~(wh ^ rot_word(sB, w, d + 1 - rho, p.xperiod)));
+                acc += __popc(~(b ^ Wj[w])) + __popc(~(wh ^ Bj[w]));
+            } else {
+                acc += __popc(~(b ^ rot_word(sB, w, d, p.xperiod))) + __popc(~(wh ^ rot_word(sW, w, d, p.xperiod)));
+                acc += __popc(~(b ^ Bj[w])) + __popc(~(wh ^ Wj[w]));
+            }
+        }
+        acc = block_sum_u64(acc);
+        if (threadIdx.x == 0) atomicAdd(equal + (j - 1), acc);
+        __syncthreads();
+    }
+}
+
+void launch_corr(const CorrParams& p, unsigned long long* equal, cudaStream_t stream)
+{
+    corr_kernel<<<p.rows, 128, 2 * (size_t)p.pitch * sizeof(uint32_t), stream>>>(p, equal);
 }
 
 // ------------------------------------------------------------------------------------------

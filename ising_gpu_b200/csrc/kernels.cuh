@@ -39,6 +39,7 @@ struct UpdateParams {
     int xperiod;            // horizontal wrap period in words
     int color;
     uint32_t zero;          // always 0; a value ptxas cannot see through (see word_reject_masks)
+    int bond_rows;          // rows of one bond plane as passed to the kernel (Y or Y+2)
 };
 
 struct InitParams {
@@ -51,8 +52,32 @@ struct InitParams {
     uint32_t zero;
 };
 
+struct BondParams {
+    uint32_t key0, key1;    // seed + 1
+    uint32_t thr;           // bond bit set iff x <= thr (uniform < prob), unless always / never
+    int always, never;
+    uint32_t grid_x, grow0;
+    long long total_rows;   // rows of the whole lattice (all slabs)
+    int rows, pitch, yperiod, xperiod;
+};
+
+constexpr int MAX_CORR_SLABS = 16;
+struct CorrParams {
+    const uint32_t* black[MAX_CORR_SLABS];   // local row 0 of every slab of the lattice (peer-mapped)
+    const uint32_t* white[MAX_CORR_SLABS];
+    int self;                                // index of the slab this launch works on
+    int rows, pitch, ncorr;
+    long long grow0;
+    long long yperiod;                       // rows per periodic unit (sub-lattice or whole lattice)
+    int xperiod;                             // words per periodic unit
+};
+
 void launch_update(const CUtensorMap& src_tile, const CUtensorMap& src_row, const CUtensorMap& src_side,
-                   uint32_t* dst_local_row0, const UpdateParams& p, int tiles_x, int tiles_y, cudaStream_t stream);
+                   uint32_t* dst_local_row0, const uint32_t* bond_planes, const UpdateParams& p, int tiles_x,
+                   int tiles_y, cudaStream_t stream);
+void launch_bond_init(uint32_t* random_planes_alloc_row0, uint32_t* mirror_planes_local_row0, const BondParams& p,
+                      cudaStream_t stream);
+void launch_corr(const CorrParams& p, unsigned long long* equal_counts, cudaStream_t stream);
 void launch_init(uint32_t* plane, const InitParams& p, cudaStream_t stream);
 // counts[0] += popcount over rows 0..rows-1 of the plane
 void launch_count(const uint32_t* plane, int rows, int pitch, unsigned long long* counts, cudaStream_t stream);

@@ -16,6 +16,7 @@ ALPHA_DEF = np.float32(0.1)            # ALPHA_DEF, optimized/main.cu:43
 BLACK, WHITE = 0, 1
 PART_ALL, PART_EDGES, PART_INTERIOR = 0, 1, 2
 F_NO_PEER_COPY = 1
+F_BONDS = 2
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
@@ -31,7 +32,7 @@ class _Cfg(C.Structure):
     _fields_ = [("X", C.c_int32), ("Y", C.c_int32), ("ndev", C.c_int32), ("first_device", C.c_int32),
                 ("seed", C.c_uint64), ("temp", C.c_float), ("xsl", C.c_int32), ("ysl", C.c_int32),
                 ("slab_first", C.c_int32), ("slab_count", C.c_int32), ("flags", C.c_int32),
-                ("reserved", C.c_int32 * 5)]
+                ("j_prob", C.c_float), ("reserved", C.c_int32 * 4)]
 
 
 def lib_path():
@@ -63,6 +64,8 @@ def load_library():
         "ising_set_temperature": ([vp, C.c_float], C.c_int),
         "ising_count_spins": ([vp, u64p, u64p], C.c_int),
         "ising_bond_sum": ([vp, C.POINTER(C.c_int64)], C.c_int),
+        "ising_correlation": ([vp, C.c_int, C.POINTER(C.c_double)], C.c_int),
+        "ising_export_bonds_ref_layout": ([vp, C.c_int, vp, vp], C.c_int),
         "ising_export_ref_layout": ([vp, C.c_int, vp, vp], C.c_int),
         "ising_import_ref_layout": ([vp, C.c_int, vp, vp], C.c_int),
         "ising_export_bits": ([vp, C.c_int, vp, vp], C.c_int),
@@ -104,7 +107,8 @@ def load_library():
 
 EXPORTED_SYMBOLS = ("ising_create ising_destroy ising_last_error ising_abi_version ising_set_stream "
                     "ising_init_lattice ising_update_color ising_sweeps ising_sync ising_sweeps_timed "
-                    "ising_set_temperature ising_count_spins ising_bond_sum ising_export_ref_layout "
+                    "ising_set_temperature ising_count_spins ising_bond_sum ising_correlation "
+                    "ising_export_bonds_ref_layout ising_export_ref_layout "
                     "ising_import_ref_layout ising_export_bits ising_import_bits ising_dump_lattice "
                     "ising_run_from_host ising_row_ptr ising_update_color_part ising_accept_count "
                     "ising_device_count ising_device_info ising_can_access_peer "
@@ -148,13 +152,16 @@ class IsingEngine:
     """One context = `ndev` slabs of Y rows x X columns driven by this process."""
 
     def __init__(self, X, Y, ndev=1, seed=DEFAULT_SEED, temp=None, alpha=None, xsl=0, ysl=0,
-                 first_device=0, slab_first=0, slab_count=0, flags=0):
+                 first_device=0, slab_first=0, slab_count=0, flags=0, j_prob=None):
         self._L = load_library()
         self.X, self.Y, self.ndev, self.seed = int(X), int(Y), int(ndev), int(seed)
         self.temp = resolve_temperature(temp, alpha)
+        if j_prob is not None:          # -J PROB, clamped as main.cu:1377
+            flags |= F_BONDS
+            j_prob = min(max(0.0, float(np.float32(j_prob))), 1.0)
         cfg = _Cfg(X=self.X, Y=self.Y, ndev=self.ndev, first_device=int(first_device), seed=self.seed,
                    temp=float(self.temp), xsl=int(xsl), ysl=int(ysl), slab_first=int(slab_first),
-                   slab_count=int(slab_count), flags=int(flags))
+                   slab_count=int(slab_count), flags=int(flags), j_prob=float(j_prob or 0.0))
         h = C.c_void_p()
         self._h = None
         self._ck(self._L.ising_create(C.byref(cfg), C.byref(h)))
@@ -233,6 +240,17 @@ class IsingEngine:
         s = C.c_int64()
         self._ck(self._L.ising_bond_sum(self._h, C.byref(s)))
         return int(s.value)
+
+    def correlation(self, ncorr=128):
+        out = (C.c_double * int(ncorr))()
+        self._ck(self._L.ising_correlation(self._h, int(ncorr), out))
+        return np.array(list(out))
+
+    def export_bonds_ref_layout(self, dev=0):
+        r = np.empty((self.Y, self.X // 32), dtype=np.uint64)
+        m = np.empty((self.Y, self.X // 32), dtype=np.uint64)
+        self._ck(self._L.ising_export_bonds_ref_layout(self._h, int(dev), _ptr(r), _ptr(m)))
+        return r, m
 
     def energy_per_site(self):
         return -self.bond_sum() / float(self.ndev * self.Y * self.X)

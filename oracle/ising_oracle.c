@@ -228,7 +228,9 @@ void ora_update_color(ora_lattice *L, int color, unsigned long long seed, int it
     const long long nwords = L->half / 32;
     const unsigned long long s = 2ull * (unsigned long long)it + (unsigned long long)color;
     const uint8_t *src = L->plane[color ^ 1];
-    const uint8_t *bnd = L->bond[color];
+    /* the reference hands the BLACK update the buffer filled by hamiltInitW_k and the WHITE
+     * update the one filled by hamiltInitB_k (main.cu:1775, :1796): kept as is */
+    const uint8_t *bnd = L->bond[color ^ 1];
     #pragma omp parallel for schedule(static)
     for (long long r = 0; r < L->rows; r++) {
         uint8_t *row = L->plane[color] + (size_t)r * L->half;
@@ -397,6 +399,97 @@ int ora_dump(const ora_lattice *L, long long row0, long long nrows, const char *
     return 0;
 }
 
+
+
+/* +-J bonds.  hamiltInitB_k (main.cu:153-212): every black site gets 4 random bits
+ * <up,down,left,right> = <8,4,2,1> from curand_init(seed+1, tid, 0); draw order per 128-bit
+ * word: nibble z = 0..15, bit l = 0..3, .x then .y -> draw index 128*j + 8*z + 2*l + h; bit set
+ * iff uniform < prob.  hamiltInitW_k (main.cu:214-331): a white site's bits mirror the bonds
+ * of its four black neighbours (its up bond is the down bond of the black site above, ...),
+ * periodic inside the sub-lattice.  The seed handed in is the run's seed; +1 is applied here. */
+int ora_init_bonds(ora_lattice *L, unsigned long long seed, float prob)
+{
+    const size_t n = (size_t)L->rows * (size_t)L->half;
+    for (int c = 0; c < 2; c++) {
+        free(L->bond[c]);
+        L->bond[c] = (uint8_t *)calloc(n, 1);
+        if (!L->bond[c]) return -1;
+    }
+    const long long nwords = L->half / 32;
+    #pragma omp parallel for schedule(static)
+    for (long long r = 0; r < L->rows; r++) {
+        uint8_t *row = L->bond[0] + (size_t)r * L->half;
+        for (long long c = 0; c < nwords; c++) {
+            const int j = (int)((c % 32) / 16);
+            const uint32_t tid = ref_tid(L, r, c);
+            for (int z = 0; z < 16; z++)
+                for (int lh = 0; lh < 2; lh++) {
+                    uint32_t x[4];
+                    const unsigned long long call = (unsigned long long)(32 * j + 2 * z + lh);
+                    const uint32_t ctr[4] = { (uint32_t)call, 0u, tid, 0u };
+                    const unsigned long long s1 = seed + 1ull;
+                    const uint32_t key[2] = { (uint32_t)s1, (uint32_t)(s1 >> 32) };
+                    ora_philox4x32_10(ctr, key, x);
+                    for (int q = 0; q < 4; q++) {          /* lane q: bit l = 2*lh + q/2, half h = q%2 */
+                        const int l = 2 * lh + q / 2, h = q % 2;
+                        if (ora_uniform(x[q]) < prob) row[32 * c + 16 * h + z] |= (uint8_t)(1u << l);
+                    }
+                }
+        }
+    }
+    /* white = mirror of the black neighbours */
+    #pragma omp parallel for schedule(static)
+    for (long long r = 0; r < L->rows; r++) {
+        uint8_t *w = L->bond[1] + (size_t)r * L->half;
+        const uint8_t *bu = L->bond[0] + (size_t)wrap_row(L, r, -1) * L->half;
+        const uint8_t *bd = L->bond[0] + (size_t)wrap_row(L, r, +1) * L->half;
+        const uint8_t *bc = L->bond[0] + (size_t)r * L->half;
+        const int odd = (int)((r + L->grow0) & 1);
+        for (long long m = 0; m < L->half; m++) {
+            /* even rows: white (col 2m+1) has black m on its left and black m+1 on its right;
+             * odd rows: white (col 2m) has black m-1 on its left and black m on its right */
+            const long long ml = odd ? wrap_col(L, m, -1) : m, mr = odd ? m : wrap_col(L, m, +1);
+            uint8_t v = 0;
+            v |= (uint8_t)(((bu[m] >> 2) & 1) << 3);    /* my up    = down bond of the black above  */
+            v |= (uint8_t)(((bd[m] >> 3) & 1) << 2);    /* my down  = up bond of the black below    */
+            v |= (uint8_t)(((bc[ml] >> 0) & 1) << 1);   /* my left  = right bond of the black left  */
+            v |= (uint8_t)(((bc[mr] >> 1) & 1) << 0);   /* my right = left bond of the black right  */
+            w[m] = v;
+        }
+    }
+    return 0;
+}
+
+uint8_t *ora_bonds(ora_lattice *L, int color) { return L->bond[color]; }
+
+/* Two-point correlation of getCorr2D_k / getCorr2DRepl_k (main.cu:870-1070) as a plain
+ * definition: out[j-1] = sum over all sites of (+1 if equal else -1) for the site j columns
+ * to the right and the site j rows below, j = 1..ncorr, periodic inside the sub-lattice,
+ * divided by 2*X*rows (computeCorr, main.cu:1129-1135).  The reference kernel equals this
+ * definition when X (or xsl) is a multiple of 4096; for other widths its chunk loop counts
+ * columns twice (chunkDimX = 4096 regardless of X) -- that quirk is not restated. */
+void ora_correlation(const ora_lattice *L, int ncorr, double *out)
+{
+    const long long X = L->X;
+    for (int j = 1; j <= ncorr; j++) {
+        long long acc = 0;
+        #pragma omp parallel for reduction(+:acc) schedule(static)
+        for (long long r = 0; r < L->rows; r++) {
+            const long long sl_r0 = (r / L->ysl) * L->ysl;
+            const long long rj = sl_r0 + (r - sl_r0 + j) % L->ysl;
+            for (long long c = 0; c < X; c++) {
+                const long long sl_c0 = (c / L->xsl) * L->xsl;
+                const long long cj = sl_c0 + (c - sl_c0 + j) % L->xsl;
+                #define SPIN(rr, cc) (L->plane[(((rr) + (cc)) & 1) ? 1 : 0][(size_t)(rr) * L->half + ((cc) >> 1)])
+                const int s = SPIN(r, c);
+                acc += (s == SPIN(r, cj)) ? 1 : -1;
+                acc += (s == SPIN(rj, c)) ? 1 : -1;
+                #undef SPIN
+            }
+        }
+        out[j - 1] = (double)acc / (2.0 * (double)X * (double)L->rows);
+    }
+}
 
 /* Streaming variant of ora_init_color + ora_count for lattices too large to hold as bytes:
  * number of up spins the reference's latticeInit_k (main.cu:92-151) produces for both

@@ -49,6 +49,10 @@ def lib():
     L.ora_import_bits.argtypes = [C.c_void_p, C.c_int, u32p]
     L.ora_dump.argtypes = [C.c_void_p, C.c_longlong, C.c_longlong, C.c_char_p]
     L.ora_num_threads.restype = C.c_int
+    L.ora_init_bonds.argtypes = [C.c_void_p, C.c_ulonglong, C.c_float]
+    L.ora_bonds.argtypes = [C.c_void_p, C.c_int]
+    L.ora_bonds.restype = C.POINTER(C.c_uint8)
+    L.ora_correlation.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double)]
     L.ora_make_slab.argtypes = [C.c_void_p, C.c_longlong]
     L.ora_ghost.argtypes = [C.c_void_p, C.c_int, C.c_int]
     L.ora_ghost.restype = C.POINTER(C.c_uint8)
@@ -163,6 +167,20 @@ class OracleLattice:
         nrows = self.rows - row0 if nrows is None else nrows
         if lib().ora_dump(self._h, int(row0), int(nrows), os.fsencode(fname)) != 0:
             raise OSError("cannot write " + fname)
+
+    def init_bonds(self, prob):
+        """-J prob: random +-J bonds (seed+1 inside, as main.cu:1734)."""
+        if lib().ora_init_bonds(self._h, self.seed, C.c_float(float(np.float32(prob)))) != 0:
+            raise MemoryError
+
+    def bonds(self, color):
+        n = self.rows * (self.X // 2)
+        return np.ctypeslib.as_array(lib().ora_bonds(self._h, int(color)), shape=(n,)).reshape(self.rows, self.X // 2)
+
+    def correlation(self, ncorr=128):
+        out = (C.c_double * ncorr)()
+        lib().ora_correlation(self._h, int(ncorr), out)
+        return np.array(list(out))
 
     def make_slab(self, grow0):
         """Hold rows [grow0, grow0+rows) of a taller lattice; edge neighbours come from ghost rows."""

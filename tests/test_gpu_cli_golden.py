@@ -12,11 +12,14 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CLI = os.path.join(ROOT, "ising_gpu_b200", "cuIsing")
 
 CASES = ["small_T1.5", "small_Tc", "rag_Tc", "sub_T1.5", "alpha_default", "seed_T2", "ramp", "mid_T1.5", "mid_Tc",
-         "big_Tc", "big_T1.5", "big_sub_T1.5", "expser", "magn_stop"]
+         "big_Tc", "big_T1.5", "big_sub_T1.5", "expser", "magn_stop", "bonds_J0.25", "bonds_J0.5_Tc", "bonds_sub",
+         "corr_sub", "corr_4096", "corr_8192_T2"]
 
 
 @pytest.mark.parametrize("case", CASES)
 def test_cli_matches_reference_transcript(case, tmp_path):
+    if case not in G.cases():
+        pytest.skip("golden case not generated")
     c = G.cases()[case]
     r = subprocess.run([CLI] + c["args"], cwd=tmp_path, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stderr[-1000:]

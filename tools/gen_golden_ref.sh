@@ -5,12 +5,20 @@
 set -u
 REF=$PWD/oracle/_ref/cuIsing_ref
 OUT=$PWD/gpurun_out/golden
+if [ "${1:-all}" = "extra" ]; then OUT=$PWD/gpurun_out/golden_extra; fi
 rm -rf $OUT; mkdir -p $OUT
 run() { # name, args...
   name=$1; shift
   mkdir -p $OUT/$name; (cd $OUT/$name && timeout 600 $REF "$@" > stdout.txt 2> stderr.txt; echo "$@" > args.txt)
   grep -E "magnetization|Kernel execution" $OUT/$name/stdout.txt | tail -3
 }
+if [ "${1:-all}" = "extra" ]; then
+run corr_4096       -x 4096 -y 1024 -n 32 -p 16 -t 2.269185 -c
+run corr_8192_T2    -x 8192 -y 512 -n 16 -p 8 -t 2.0 -c -s 987654321
+run bonds_sub       -x 4096 -y 64 -n 4 -p 2 -t 1.5 -J 0.3 --xsl 2048 --ysl 32 -o
+tar czf $PWD/gpurun_out/golden_extra.tgz -C $PWD/gpurun_out golden
+exit 0
+fi
 run small_T1.5      -x 2048 -y 16 -n 4 -p 1 -t 1.5 -o
 run small_Tc        -x 2048 -y 16 -n 4 -p 1 -t 2.269185 -o
 run rag_Tc          -x 6144 -y 48 -n 3 -p 1 -t 2.269185 -o

@@ -14,8 +14,8 @@ DST = os.path.join(ROOT, "tests", "golden")
 os.makedirs(DST, exist_ok=True)
 index = {}
 tar = tarfile.open(os.path.join(DST, "reference_b200_files.tgz"), "w:gz", compresslevel=9)
-for case in sorted(os.listdir(SRC)):
-    d = os.path.join(SRC, case)
+SRCS = [SRC, os.path.join(ROOT, "gpurun_out", "golden_extra")]
+for case, d in sorted((c, os.path.join(sd, c)) for sd in SRCS if os.path.isdir(sd) for c in os.listdir(sd)):
     out = open(os.path.join(d, "stdout.txt")).read()
     entry = {"args": open(os.path.join(d, "args.txt")).read().split(), "lines": [], "files": []}
     for ln in out.splitlines():
