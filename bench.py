@@ -35,6 +35,7 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+_GUARD = None
 X_COLS = 65536
 TEMP = 1.5
 ALG_BYTES_PER_FLIP = 0.25      # each spin read once + written once per sweep at 1 bit/spin
@@ -255,7 +256,7 @@ def run_b200(a):
         dist.destroy_process_group()
     eng.close()
     if rank == 0:
-        print(json.dumps(out), flush=True)
+        _GUARD.emit(json.dumps(out))
 
 
 def run_reference(a):
@@ -298,7 +299,7 @@ def run_reference(a):
                                           "sample": "GPU reference binary, not a CPU run: %d sweeps of the full "
                                                     "workload" % (S * a.steps)},
                          "e2e": {"value": fl, "unit": "flips/ns", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
-            print(json.dumps(base), flush=True)
+            _GUARD.emit(json.dumps(base))
             return
         except Exception as e:   # fall through to the CPU port
             base["reference_gpu_error"] = str(e)[:300]
@@ -319,7 +320,21 @@ def run_reference(a):
                                   "kind": "port", "sample": "C/OpenMP oracle, %d rows x %d, 1 sweep per step" %
                                   (srows, X_COLS)},
                  "e2e": {"value": round(fl, 4), "unit": "flips/ns", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
-    print(json.dumps(base), flush=True)
+    _GUARD.emit(json.dumps(base))
+
+
+class _StdoutGuard:
+    """Everything libraries print to fd 1 (e.g. NCCL's version banner) goes to stderr; only the
+    final JSON line reaches the real stdout."""
+
+    def __init__(self):
+        sys.stdout.flush()
+        self.real = os.dup(1)
+        os.dup2(2, 1)
+
+    def emit(self, line):
+        sys.stdout.flush()
+        os.write(self.real, (line + "\n").encode())
 
 
 def main():
@@ -337,6 +352,8 @@ def main():
     ap.add_argument("--no-overlap", action="store_true")
     ap.add_argument("--ref-cpu", action="store_true", help="reference arm: force the CPU oracle port")
     a = ap.parse_args()
+    global _GUARD
+    _GUARD = _StdoutGuard()
     if a.warmup < 3 and a.impl == "b200":
         a.warmup = 3   # timing rule: at least 3 warm-up steps
     if a.impl == "reference":
