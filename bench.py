@@ -150,7 +150,8 @@ def run_b200(a):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     rows = a.rows_per_gpu or default_rows(world)
     S = a.sweeps_per_step
-    eng = SlabEngine(X_COLS, rows, TEMP, a.seed, rank=rank, world=world, device=local, overlap=not a.no_overlap)
+    eng = SlabEngine(X_COLS, rows, TEMP, a.seed, rank=rank, world=world, device=local, overlap=not a.no_overlap,
+                     halo=a.halo)
 
     def barrier():
         torch.cuda.synchronize()
@@ -195,9 +196,7 @@ def run_b200(a):
 
         def e2e_step():
             eng.eng.import_bits(nb, nw)          # H2D of both colour planes (pinned)
-            if world > 1:
-                for color in (0, 1):              # ghost rows belong to the uploaded state
-                    eng._exchange_blocking(color)
+            eng.refresh_ghosts()                  # ghost rows belong to the uploaded state
             eng.sweeps(S)
             eng.eng._ck(eng.eng._L.ising_export_bits(eng.eng._h, 0, nb.ctypes.data, nw.ctypes.data))  # D2H
             return eng.count_spins()              # D2H of the step's observable
@@ -240,8 +239,11 @@ def run_b200(a):
                                       "%d sweeps per step" % (rows * world, X_COLS, rows, TEMP, a.seed, S),
                           "lattice_bytes_per_gpu": rows * X_COLS // 8, "l2_flush": "inputs larger than L2 "
                           "(%d MiB of spins per GPU vs 126 MB L2)" % (rows * X_COLS // 8 >> 20),
-                          "halo": "none" if world == 1 else ("NCCL send/recv of 1 row per direction per colour, "
-                                  + ("overlapped with the interior update" if not a.no_overlap else "serialised"))},
+                          "halo": "none" if world == 1 else (
+                              "fused: update kernel stores its edge rows into the neighbours' ghost rows (CUDA IPC "
+                              "peer memory over NVLink) and signals device-side counters" if a.halo == "fused" else
+                              "NCCL send/recv of 1 row per direction per colour, " +
+                              ("overlapped with the interior update" if not a.no_overlap else "serialised"))},
                "roofline": roof, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
                "final_counts": {"up": up if world == 1 else None, "down": dn if world == 1 else None}}
         if world == 1 and not a.no_cpu:
@@ -350,6 +352,9 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-overlap", action="store_true")
+    ap.add_argument("--halo", default="fused", choices=["fused", "nccl"],
+                    help="fused: the update kernel stores boundary rows into the neighbours' ghost rows over NVLink "
+                         "(CUDA IPC peer memory); nccl: NCCL send/recv per colour")
     ap.add_argument("--ref-cpu", action="store_true", help="reference arm: force the CPU oracle port")
     a = ap.parse_args()
     global _GUARD

@@ -168,6 +168,19 @@ int ising_device_info(int device, char* name, size_t name_len, int* sms, int* ma
 /* *ok = 1 when `device` can map `peer`'s memory (cudaDeviceCanAccessPeer) */
 int ising_can_access_peer(int device, int peer, int* ok);
 
+/* Fused halo push between processes: the update kernel of a slab stores its first/last row
+ * straight into the neighbouring slabs' ghost rows (NVLink peer stores) and signals a counter in
+ * their memory; no NCCL / copy-engine / host step per colour.  Each rank exports CUDA IPC handles
+ * (3 x 64 bytes: black plane, white plane, counters), ships them to its ring neighbours by any
+ * means (bench.py: torch.distributed all_gather) and attaches the two neighbours' handles.  After
+ * attach, ising_push_edges(color) fills the neighbours' ghost rows once (init / import; follow it
+ * with a barrier between the ranks), then ising_update_color / ising_sweeps need no further help.
+ * Single-process contexts with ndev > 1 use the same kernel path through peer access
+ * automatically (set ISING_B200_HALO=copy to fall back to cudaMemcpyPeerAsync per colour). */
+int ising_ipc_export(ising_ctx* ctx, void* handles, size_t nbytes);
+int ising_ipc_attach(ising_ctx* ctx, const void* up_handles, const void* down_handles);
+int ising_push_edges(ising_ctx* ctx, int color);
+
 /* ---- introspection used by tests and bench ----------------------------------------------*/
 /* Number of 32-bit Philox outputs x accepted by `uniform(x) <= p` (strict = 0) or
  * `uniform(x) < p` (strict = 1), uniform(x) = x*2^-32 + 2^-33 in float (curand_uniform).

@@ -64,6 +64,14 @@ struct DevState {
     uint32_t* bond_mirror = nullptr;           // 4 planes x Y x pitch (hamiltInitW_k)
     unsigned long long* d_corr = nullptr;
     unsigned long long* d_counts = nullptr;    // [0] up-count, [1] unequal bonds
+    // fused halo push: arrival counters written by the neighbours (recv_top[2], recv_bot[2]) and
+    // the neighbours' planes / counters as seen from this device (peer access or CUDA IPC)
+    unsigned int* d_flags = nullptr;
+    uint32_t* up_plane[2] = {nullptr, nullptr};
+    uint32_t* dn_plane[2] = {nullptr, nullptr};
+    unsigned int* up_flags = nullptr;
+    unsigned int* dn_flags = nullptr;
+    void* ipc_opened[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t ev_color = nullptr;            // kernel + halo pushes of the last colour issued
     cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;
 };
@@ -75,6 +83,8 @@ struct ising_ctx {
     int pitch = 0;        // 32-site words per colour row = X/64
     int slab_count = 1;
     bool bonds = false;
+    bool fused = false;       // halo rows are pushed by the update kernel itself (peer stores + counters)
+    uint64_t pushes_done[2] = {0, 0};
     bool peer_halo = false;   // library copies boundary rows between its own devices
     bool ghost_rows = false;  // vertical neighbours of the slab edge come from ghost rows
     int yperiod = 0, xperiod = 0;
@@ -154,6 +164,18 @@ int launch_part(ising_ctx* c, int dev, int color, int it, int part, cudaStream_t
     } else if (part == ISING_PART_INTERIOR) {
         p.tile_row0 = 1; gy = tiles_y - 2;
         if (gy <= 0) return ISING_OK;
+    }
+    if (c->fused) {
+        if (part != ISING_PART_ALL) return fail(ISING_ESTATE, "edge/interior parts are not used with the fused halo push");
+        const int Y = c->cfg.Y;
+        p.push = 1;
+        p.push_up = d.up_plane[color] + (size_t)(Y + 1) * c->pitch;   // neighbour above: its bottom ghost row
+        p.push_dn = d.dn_plane[color];                                // neighbour below: its top ghost row
+        p.sig_up = d.up_flags + 2 + color;                            // its recv_bot[color]
+        p.sig_dn = d.dn_flags + 0 + color;                            // its recv_top[color]
+        p.wait_top = d.d_flags + 0 + src;
+        p.wait_bot = d.d_flags + 2 + src;
+        p.wait_value = (unsigned int)(c->pushes_done[src] * (uint64_t)tiles_x);
     }
     CU_TRY(cudaSetDevice(d.device));
     // the reference hands the BLACK update the hamiltInitW_k buffer and the WHITE update the
@@ -313,6 +335,11 @@ int ising_create(const ising_cfg* cfg, ising_ctx** out)
             if ((rc = make_map(&d.map_side[col], d.plane[col], c->pitch, cfg->Y + 2, SIDE_W, TH))) return cleanup(rc);
         }
         if ((e = cudaMalloc(&d.d_counts, 2 * sizeof(unsigned long long))) != cudaSuccess) return cleanup(fail(ISING_ENOMEM, "%s", cudaGetErrorString(e)));
+        if (c->ghost_rows) {
+            if ((e = cudaMalloc(&d.d_flags, 8 * sizeof(unsigned int))) != cudaSuccess ||
+                (e = cudaMemsetAsync(d.d_flags, 0, 8 * sizeof(unsigned int), d.stream)) != cudaSuccess)
+                return cleanup(fail(ISING_ENOMEM, "flags: %s", cudaGetErrorString(e)));
+        }
         if (c->bonds) {
             if ((e = cudaMalloc(&d.bond_random, 4 * plane_bytes)) != cudaSuccess ||
                 (e = cudaMalloc(&d.bond_mirror, 4 * (size_t)cfg->Y * c->pitch * 4)) != cudaSuccess)
@@ -322,6 +349,18 @@ int ising_create(const ising_cfg* cfg, ising_ctx** out)
             (e = cudaEventCreate(&d.ev_t0)) != cudaSuccess || (e = cudaEventCreate(&d.ev_t1)) != cudaSuccess)
             return cleanup(fail(ISING_ECUDA, "event: %s", cudaGetErrorString(e)));
         if ((e = cudaStreamSynchronize(d.stream)) != cudaSuccess) return cleanup(fail(ISING_ECUDA, "%s", cudaGetErrorString(e)));
+    }
+    if (c->peer_halo) {   // single process: neighbours are reachable through peer access
+        const char* mode = getenv("ISING_B200_HALO");
+        const int n = cfg->ndev;
+        for (int i = 0; i < n; i++) {
+            DevState& d = c->dev[i];
+            DevState& u = c->dev[(i + n - 1) % n];
+            DevState& w = c->dev[(i + 1) % n];
+            for (int col = 0; col < 2; col++) { d.up_plane[col] = u.plane[col]; d.dn_plane[col] = w.plane[col]; }
+            d.up_flags = u.d_flags; d.dn_flags = w.d_flags;
+        }
+        c->fused = !(mode && strcmp(mode, "copy") == 0);   // "copy": cudaMemcpyPeerAsync + events per colour
     }
     *out = c;
     return ISING_OK;
@@ -338,6 +377,8 @@ int ising_destroy(ising_ctx* c)
         if (d.bond_random) cudaFree(d.bond_random);
         if (d.bond_mirror) cudaFree(d.bond_mirror);
         if (d.d_corr) cudaFree(d.d_corr);
+        if (d.d_flags) cudaFree(d.d_flags);
+        for (void* q : d.ipc_opened) if (q) cudaIpcCloseMemHandle(q);
         if (d.ev_color) cudaEventDestroy(d.ev_color);
         if (d.ev_t0) cudaEventDestroy(d.ev_t0);
         if (d.ev_t1) cudaEventDestroy(d.ev_t1);
@@ -488,7 +529,65 @@ int ising_update_color(ising_ctx* c, int color, int it)
     if (!c || (color != 0 && color != 1)) return fail(ISING_EINVAL, "bad argument");
     for (int i = 0; i < (int)c->dev.size(); i++)
         if (int rc = launch_part(c, i, color, it, ISING_PART_ALL, c->dev[i].stream)) return rc;
+    if (c->fused) { c->pushes_done[color]++; return ISING_OK; }
     if (c->peer_halo) return push_halo(c, color);
+    return ISING_OK;
+}
+
+int ising_ipc_export(ising_ctx* c, void* handles, size_t nbytes)
+{
+    if (!c || c->dev.size() != 1 || !handles || nbytes < 3 * sizeof(cudaIpcMemHandle_t))
+        return fail(ISING_EINVAL, "ising_ipc_export: 1-device context and a buffer of %zu bytes needed", 3 * sizeof(cudaIpcMemHandle_t));
+    if (!c->ghost_rows) return fail(ISING_ESTATE, "context is not a slab of a larger lattice");
+    DevState& d = c->dev[0];
+    CU_TRY(cudaSetDevice(d.device));
+    cudaIpcMemHandle_t* h = (cudaIpcMemHandle_t*)handles;
+    CU_TRY(cudaIpcGetMemHandle(&h[0], d.plane[0]));
+    CU_TRY(cudaIpcGetMemHandle(&h[1], d.plane[1]));
+    CU_TRY(cudaIpcGetMemHandle(&h[2], d.d_flags));
+    return ISING_OK;
+}
+
+int ising_ipc_attach(ising_ctx* c, const void* up_handles, const void* dn_handles)
+{
+    if (!c || c->dev.size() != 1 || !up_handles || !dn_handles) return fail(ISING_EINVAL, "bad argument");
+    if (!c->ghost_rows) return fail(ISING_ESTATE, "context is not a slab of a larger lattice");
+    DevState& d = c->dev[0];
+    CU_TRY(cudaSetDevice(d.device));
+    const cudaIpcMemHandle_t* hu = (const cudaIpcMemHandle_t*)up_handles;
+    const cudaIpcMemHandle_t* hd = (const cudaIpcMemHandle_t*)dn_handles;
+    void* pu[3];
+    void* pd[3];
+    for (int k = 0; k < 3; k++) {
+        CU_TRY(cudaIpcOpenMemHandle(&pu[k], hu[k], cudaIpcMemLazyEnablePeerAccess));
+        d.ipc_opened[k] = pu[k];
+    }
+    const bool same = memcmp(hu, hd, 3 * sizeof(cudaIpcMemHandle_t)) == 0;   // 2 slabs: one neighbour is both
+    for (int k = 0; k < 3; k++) {
+        if (same) pd[k] = pu[k];
+        else { CU_TRY(cudaIpcOpenMemHandle(&pd[k], hd[k], cudaIpcMemLazyEnablePeerAccess)); d.ipc_opened[3 + k] = pd[k]; }
+    }
+    d.up_plane[0] = (uint32_t*)pu[0]; d.up_plane[1] = (uint32_t*)pu[1]; d.up_flags = (unsigned int*)pu[2];
+    d.dn_plane[0] = (uint32_t*)pd[0]; d.dn_plane[1] = (uint32_t*)pd[1]; d.dn_flags = (unsigned int*)pd[2];
+    c->fused = true;
+    return ISING_OK;
+}
+
+// Store this slab's first/last row of `color` into the neighbours' ghost rows with peer stores
+// (initial fill after init/import; the sweep loop pushes from inside the update kernel).
+int ising_push_edges(ising_ctx* c, int color)
+{
+    if (!c || (color != 0 && color != 1)) return fail(ISING_EINVAL, "bad argument");
+    if (!c->fused) return fail(ISING_ESTATE, "fused halo push is not enabled on this context");
+    const size_t row_bytes = (size_t)c->pitch * 4;
+    for (DevState& d : c->dev) {
+        CU_TRY(cudaSetDevice(d.device));
+        CU_TRY(cudaMemcpyAsync(d.up_plane[color] + (size_t)(c->cfg.Y + 1) * c->pitch, local_row(c, d, color, 0), row_bytes,
+                               cudaMemcpyDefault, d.stream));
+        CU_TRY(cudaMemcpyAsync(d.dn_plane[color], local_row(c, d, color, c->cfg.Y - 1), row_bytes, cudaMemcpyDefault,
+                               d.stream));
+        CU_TRY(cudaStreamSynchronize(d.stream));
+    }
     return ISING_OK;
 }
 

@@ -60,6 +60,13 @@ __device__ __forceinline__ void tma_store_commit_wait()
 }
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+__device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int* p)
+{
+    unsigned int v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
 // acc = 2*acc + (x > thr): x + ~thr carries out of 32 bits exactly when x > thr; the carry
 // flag is shifted in by the add-with-carry (IADD3 + IADD3.X / IMAD.X in SASS).  Rejected
 // sites accumulate as 1 bits.  nthr = ~thr.
@@ -260,7 +267,7 @@ __device__ __forceinline__ uint32_t flip_mask(uint32_t me, uint32_t up, uint32_t
 #ifndef ISING_MIN_BLOCKS
 #define ISING_MIN_BLOCKS 4
 #endif
-template <bool FAST, bool BONDS>
+template <bool FAST, bool BONDS, bool PUSH>
 __global__ void __launch_bounds__(UPDATE_THREADS, ISING_MIN_BLOCKS)
 update_color_kernel(const __grid_constant__ CUtensorMap src_tile, const __grid_constant__ CUtensorMap src_row,
                     const __grid_constant__ CUtensorMap src_side, uint32_t* __restrict__ dst /* local row 0 */,
@@ -272,7 +279,10 @@ update_color_kernel(const __grid_constant__ CUtensorMap src_tile, const __grid_c
     __shared__ alignas(128) uint32_t sR[TH * SIDE_W];
     __shared__ alignas(8) uint64_t bar;
 
-    const int tile_row = p.edges_mode ? (blockIdx.y == 0 ? p.tile_row0 : p.tile_row_alt) : p.tile_row0 + (int)blockIdx.y;
+    int tile_row;
+    if (p.edges_mode) tile_row = (blockIdx.y == 0) ? p.tile_row0 : p.tile_row_alt;
+    else if (PUSH)    tile_row = (blockIdx.y == 0) ? 0 : ((blockIdx.y == 1) ? (int)gridDim.y - 1 : (int)blockIdx.y - 1);
+    else              tile_row = p.tile_row0 + (int)blockIdx.y;
     const int x0 = blockIdx.x * TW;       // first word of the tile in the row
     const int y0 = tile_row * TH;         // first local row of the tile
     const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
@@ -299,6 +309,11 @@ update_color_kernel(const __grid_constant__ CUtensorMap src_tile, const __grid_c
     }
     __syncthreads();
     if (threadIdx.x == 0) {
+        if (PUSH) {   // ghost rows of the source colour must have arrived from the neighbours
+            if (y0 == 0) while ((int)(ld_acquire_sys(p.wait_top) - p.wait_value) < 0) { }
+            if (y0 + TH == p.rows) while ((int)(ld_acquire_sys(p.wait_bot) - p.wait_value) < 0) { }
+            asm volatile("fence.proxy.async;" ::: "memory");   // later TMA reads see the peer's stores
+        }
         int ytop, ybot;
         if (p.yperiod > 0) {
             ytop = (y0 % p.yperiod == 0) ? y0 + p.yperiod - 1 : y0 - 1;
@@ -356,7 +371,19 @@ update_color_kernel(const __grid_constant__ CUtensorMap src_tile, const __grid_c
             if (read_back) { sd ^= jb[j][2]; ct ^= jb[j][3]; }   // sd = left neighbour, ct = right
             else           { ct ^= jb[j][2]; sd ^= jb[j][3]; }   // ct = left neighbour, sd = right
         }
-        my[16 * j] = me[j] ^ flip_mask<FAST>(me[j], up, dn, ct, sd, rejA[j], rejB[j], p.rule);
+        me[j] ^= flip_mask<FAST>(me[j], up, dn, ct, sd, rejA[j], rejB[j], p.rule);
+        my[16 * j] = me[j];
+    }
+    if (PUSH && (y0 == 0 || y0 + TH == p.rows)) {   // CTA-uniform: only the two edge tile rows push
+        const int row = y0 + ty;
+        const bool top = (row == 0), bot = (row == p.rows - 1);
+        if (top) { p.push_up[x0 + tx] = me[0]; p.push_up[x0 + tx + 16] = me[1]; }
+        if (bot) { p.push_dn[x0 + tx] = me[0]; p.push_dn[x0 + tx + 16] = me[1]; }
+        if (top || bot) __threadfence_system();
+        __syncwarp();
+        // rows 0 and Y-1 are written by the half-warps ty == 0 (threads 0..15) and ty == 15 (240..255)
+        if (top && tx == 0) atomicAdd_system(p.sig_up, 1u);
+        if (bot && tx == 0) atomicAdd_system(p.sig_dn, 1u);
     }
 }
 
@@ -365,17 +392,20 @@ void launch_update(const CUtensorMap& src_tile, const CUtensorMap& src_row, cons
                    cudaStream_t stream)
 {
     const dim3 grid((unsigned)tiles_x, (unsigned)tiles_y);
-    if (bonds) {
-        if (p.rule.fast)
-            update_color_kernel<true, true><<<grid, UPDATE_THREADS, 0, stream>>>(src_tile, src_row, src_side, dst, bonds, p);
-        else
-            update_color_kernel<false, true><<<grid, UPDATE_THREADS, 0, stream>>>(src_tile, src_row, src_side, dst, bonds, p);
-    } else {
-        if (p.rule.fast)
-            update_color_kernel<true, false><<<grid, UPDATE_THREADS, 0, stream>>>(src_tile, src_row, src_side, dst, nullptr, p);
-        else
-            update_color_kernel<false, false><<<grid, UPDATE_THREADS, 0, stream>>>(src_tile, src_row, src_side, dst, nullptr, p);
+#define ISING_LAUNCH(F, B, P) \
+    update_color_kernel<F, B, P><<<grid, UPDATE_THREADS, 0, stream>>>(src_tile, src_row, src_side, dst, bonds, p)
+    const int sel = (p.rule.fast ? 4 : 0) | (bonds ? 2 : 0) | (p.push ? 1 : 0);
+    switch (sel) {
+        case 0: ISING_LAUNCH(false, false, false); break;
+        case 1: ISING_LAUNCH(false, false, true); break;
+        case 2: ISING_LAUNCH(false, true, false); break;
+        case 3: ISING_LAUNCH(false, true, true); break;
+        case 4: ISING_LAUNCH(true, false, false); break;
+        case 5: ISING_LAUNCH(true, false, true); break;
+        case 6: ISING_LAUNCH(true, true, false); break;
+        default: ISING_LAUNCH(true, true, true); break;
     }
+#undef ISING_LAUNCH
 }
 
 const char* update_kernel_name(int fast)

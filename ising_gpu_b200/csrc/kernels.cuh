@@ -40,6 +40,18 @@ struct UpdateParams {
     int color;
     uint32_t zero;          // always 0; a value ptxas cannot see through (see word_reject_masks)
     int bond_rows;          // rows of one bond plane as passed to the kernel (Y or Y+2)
+    // Fused halo push (multi-slab, peer-mapped neighbours): the CTAs owning the slab's first / last
+    // row store the new row into the neighbour's ghost row as well and count themselves done on the
+    // neighbour's arrival counter; before reading their own ghost row they wait for the neighbour's
+    // CTAs of the previous colour step.  No host, copy engine or NCCL call in the sweep loop.
+    int push;               // 0 = off; 1 = on; edges are then scheduled first (blockIdx.y 0 and 1)
+    uint32_t* push_up;      // neighbour above: its bottom ghost row of the colour being updated
+    uint32_t* push_dn;      // neighbour below: its top ghost row
+    unsigned int* sig_up;   // arrival counter in the neighbour above (its "bottom ghost ready")
+    unsigned int* sig_dn;   // arrival counter in the neighbour below (its "top ghost ready")
+    const unsigned int* wait_top;   // own counters for the SOURCE colour's ghost rows
+    const unsigned int* wait_bot;
+    unsigned int wait_value;        // pushes the neighbours must have completed: steps * tiles_x
 };
 
 struct InitParams {

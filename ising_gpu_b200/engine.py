@@ -77,6 +77,9 @@ def load_library():
         "ising_device_count": ([C.POINTER(C.c_int)], C.c_int),
         "ising_device_info": ([C.c_int, C.c_char_p, C.c_size_t] + [C.POINTER(C.c_int)] * 5, C.c_int),
         "ising_can_access_peer": ([C.c_int, C.c_int, C.POINTER(C.c_int)], C.c_int),
+        "ising_ipc_export": ([vp, vp, C.c_size_t], C.c_int),
+        "ising_ipc_attach": ([vp, vp, vp], C.c_int),
+        "ising_push_edges": ([vp, C.c_int], C.c_int),
         "ising_accept_count": ([C.c_float, C.c_int], C.c_uint64),
         "ising_accept_table": ([C.c_float, C.POINTER(C.c_float)], None),
         "ising_site_random": ([C.c_uint64, C.c_int32, C.c_int, C.c_int, C.c_uint32, C.c_uint32, C.c_int, u32p], None),
@@ -112,6 +115,7 @@ EXPORTED_SYMBOLS = ("ising_create ising_destroy ising_last_error ising_abi_versi
                     "ising_import_ref_layout ising_export_bits ising_import_bits ising_dump_lattice "
                     "ising_run_from_host ising_row_ptr ising_update_color_part ising_accept_count "
                     "ising_device_count ising_device_info ising_can_access_peer "
+                    "ising_ipc_export ising_ipc_attach ising_push_edges "
                     "ising_accept_table ising_site_random ising_launch_count ising_kernel_name "
                     "ising_tc_create ising_tc_destroy ising_tc_set_nn_path ising_tc_init ising_tc_update "
                     "ising_tc_update_timed ising_tc_sync ising_tc_sum ising_tc_export_storage "
@@ -289,6 +293,17 @@ class IsingEngine:
                                              C.byref(up) if counts else None, C.byref(dn) if counts else None))
         self.it += int(n)
         return int(up.value), int(dn.value)
+
+    def ipc_export(self):
+        buf = C.create_string_buffer(192)
+        self._ck(self._L.ising_ipc_export(self._h, buf, 192))
+        return buf.raw
+
+    def ipc_attach(self, up_handles, down_handles):
+        self._ck(self._L.ising_ipc_attach(self._h, C.c_char_p(up_handles), C.c_char_p(down_handles)))
+
+    def push_edges(self, color):
+        self._ck(self._L.ising_push_edges(self._h, int(color)))
 
     def row_ptr(self, dev, color, row):
         p, n = C.c_void_p(), C.c_size_t()

@@ -82,8 +82,12 @@ class GpuSlab:
 class SlabEngine:
     """What bench.py and the multi-GPU tests drive: init + sweeps with overlapped halo exchange."""
 
-    def __init__(self, X, Y, temp, seed, rank=0, world=1, device=0, group=None, overlap=True):
+    def __init__(self, X, Y, temp, seed, rank=0, world=1, device=0, group=None, overlap=True, halo="nccl"):
+        """halo = "nccl": boundary rows travel as NCCL send/recv (overlapped with the interior when
+        `overlap`); "fused": the update kernel stores them into the neighbours' ghost rows itself
+        through CUDA-IPC-mapped peer memory (ising_ipc_attach), no per-colour communication call."""
         self.rank, self.world, self.overlap = rank, world, overlap
+        self.fused = (halo == "fused") and world > 1
         torch.cuda.set_device(device)
         self.main = torch.cuda.current_stream()
         self.comm = torch.cuda.Stream() if world > 1 else None
@@ -97,12 +101,34 @@ class SlabEngine:
     def _exchange_blocking(self, color):
         HaloExchange.finish(self.halo.start(self.slab, color))
 
+    def _attach_peers(self):
+        mine = self.eng.ipc_export()
+        allh = [None] * self.world
+        dist.all_gather_object(allh, mine, group=self.halo.group)
+        self.eng.ipc_attach(allh[self.halo.up], allh[self.halo.down])
+        self._attached = True
+
+    def refresh_ghosts(self):
+        """Fill the ghost rows from the neighbours' current edge rows (after init / import)."""
+        if self.world == 1:
+            return
+        if self.fused:
+            torch.cuda.synchronize()
+            dist.barrier(group=self.halo.group)         # everybody's rows are final
+            for color in (0, 1):
+                self.eng.push_edges(color)
+            torch.cuda.synchronize()
+            dist.barrier(group=self.halo.group)         # everybody's ghosts are filled
+        else:
+            for color in (0, 1):
+                self._exchange_blocking(color)
+
     def init_lattice(self):
         self.eng.init_lattice()
         self.it = 0
-        if self.world > 1:
-            for color in (0, 1):
-                self._exchange_blocking(color)
+        if self.fused and not getattr(self, "_attached", False):
+            self._attach_peers()
+        self.refresh_ghosts()
 
     def _half_sweep(self, color, it):
         if self.world == 1:
@@ -123,6 +149,10 @@ class SlabEngine:
         self.slab.update(color, it, PART_INTERIOR)
 
     def sweeps(self, n):
+        if self.fused:                       # one kernel per colour, halo pushed from inside it
+            self.eng._ck(self.eng._L.ising_sweeps(self.eng._h, self.it + 1, int(n)))
+            self.it += int(n)
+            return
         for _ in range(n):
             self.it += 1
             self._half_sweep(0, self.it)

@@ -14,7 +14,8 @@ X, Y, sweeps, temp, overlap, out = int(sys.argv[1]), int(sys.argv[2]), int(sys.a
 rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
 torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-eng = SlabEngine(X, Y, temp, 463463564571, rank=rank, world=world, device=local, overlap=bool(overlap))
+halo = "fused" if overlap == 2 else "nccl"
+eng = SlabEngine(X, Y, temp, 463463564571, rank=rank, world=world, device=local, overlap=bool(overlap), halo=halo)
 eng.init_lattice()
 eng.sweeps(sweeps)
 torch.cuda.synchronize()

@@ -68,10 +68,12 @@ def test_slabs_on_one_gpu_with_manual_halo(ig, oracle, nslab, Y):
         e.close()
 
 
-def test_single_process_two_devices(ig, oracle):
-    """cuIsing -d 2 path: one context, two GPUs, library-managed peer copies."""
+@pytest.mark.parametrize("mode", ["fused", "copy"])
+def test_single_process_two_devices(ig, oracle, mode, monkeypatch):
+    """cuIsing -d 2 path: one context, two GPUs; halo pushed by the kernel (default) or copied."""
     if _ngpu() < 2:
         pytest.skip("needs 2 GPUs")
+    monkeypatch.setenv("ISING_B200_HALO", mode)
     X, Y, sweeps = 4096, 64, 4
     with ig.IsingEngine(X, Y, ndev=2, temp=TC) as eng:
         eng.init_lattice()
@@ -83,9 +85,10 @@ def test_single_process_two_devices(ig, oracle):
         assert eng.count_spins() == cnt
 
 
-@pytest.mark.parametrize("overlap", [1, 0])
+@pytest.mark.parametrize("overlap", [1, 0, 2])
 def test_one_process_per_gpu_nccl(oracle, tmp_path, overlap):
-    """torchrun, 2 ranks, NCCL halo (overlapped and serialised): stacked slabs == oracle."""
+    """torchrun, 2 ranks; halo over NCCL (1 overlapped, 0 serialised) or pushed by the update kernel
+    itself through CUDA-IPC peer memory (2): stacked slabs == oracle."""
     if _ngpu() < 2:
         pytest.skip("needs 2 GPUs")
     X, Y, sweeps = 4096, 64, 5
