@@ -472,8 +472,6 @@ int ising_correlation(ising_ctx* c, int ncorr, double* out)
         if (!d.d_corr) CU_TRY(cudaMalloc(&d.d_corr, 4096 * sizeof(unsigned long long)));
         CU_TRY(cudaMemsetAsync(d.d_corr, 0, ncorr * sizeof(unsigned long long), d.stream));
         p.self = i; p.grow0 = (long long)i * c->cfg.Y;
-        static bool attr = false;
-        (void)attr;
         launch_corr(p, d.d_corr, d.stream);
         CU_TRY(cudaGetLastError());
         c->launches++;

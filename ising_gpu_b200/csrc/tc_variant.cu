@@ -20,6 +20,7 @@
 #include <string>
 #include <vector>
 
+#include <cuda.h>
 #include <cuda_runtime.h>
 
 #include "../../include/ising_b200.h"
@@ -133,16 +134,15 @@ __global__ void __launch_bounds__(SUBN) tc_update_stencil_kernel(int8_t* __restr
 // registers, where the 16 runs of 8 spins are updated with the reference's RNG map.
 // ------------------------------------------------------------------------------------------
 constexpr int TILE_BYTES = SUBN * SUBN;   // 16 KiB per operand tile
-__device__ __forceinline__ int img(int row, int byte)
-{
-    return (row >> 3) * 1024 + (byte >> 4) * 128 + (row & 7) * 16 + (byte & 15);
-}
 __device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo)
+// SWIZZLE_128B operand descriptor: rows of 128 bytes, 8-row groups 1024 bytes apart (SBO), the
+// 16-byte chunk index of every row XORed with (row % 8) -- exactly what a TMA load with
+// CU_TENSOR_MAP_SWIZZLE_128B of a 128-byte-wide box leaves in shared memory.
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr)
 {
-    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) |
-           (1ull << 46);   // version 1 (sm_100), SWIZZLE_NONE, base offset 0
+    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) |
+           (2ull << 61);
 }
 __host__ __device__ constexpr uint32_t IDESC_I8(int a_mn_major, int b_mn_major)
 {
@@ -164,15 +164,42 @@ __device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t da, uint64_t d
 
 constexpr int MMA_THREADS = 256;   // warps w and w+4 share TMEM lanes 32(w%4).., split the 128 columns
 
-template <bool WRITE_NN, bool FAST>
-__global__ void __launch_bounds__(MMA_THREADS, 3) tc_update_mma_kernel(int8_t* __restrict__ lat, int8_t* __restrict__ nn_out,
-                                                                      const __grid_constant__ TcParams p)
+__device__ __forceinline__ void tma_load_rows(void* dst, const CUtensorMap* map, int row, uint64_t* bar)
 {
-    extern __shared__ __align__(1024) uint8_t smem[];
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+                     smem_addr(dst)),
+                 "l"(map), "r"(0), "r"(row), "r"(smem_addr(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait_parity0(uint64_t* bar)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "W_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n"
+        "@p bra D_%=;\n"
+        "bra W_%=;\n"
+        "D_%=:\n"
+        "}\n" ::"r"(smem_addr(bar))
+        : "memory");
+}
+
+// lat_map: the lattice as (n/128) rows of 128 bytes, box 128 x 128, SWIZZLE_128B -- one box = one
+// sub-block.  k_map: the four constant bidiagonal matrices (512 rows of 128 bytes), same box.
+template <bool WRITE_NN, bool FAST>
+__global__ void __launch_bounds__(MMA_THREADS, 3)
+tc_update_mma_kernel(const __grid_constant__ CUtensorMap lat_map, const __grid_constant__ CUtensorMap k_map,
+                     int8_t* __restrict__ lat, int8_t* __restrict__ nn_out, const __grid_constant__ TcParams p)
+{
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    // 128-byte swizzle atoms must start on 1024-byte boundaries of the shared address space
+    uint8_t* smem = smem_raw + ((1024u - (smem_addr(smem_raw) & 1023u)) & 1023u);
     uint8_t* sH = smem;
     uint8_t* sV = smem + TILE_BYTES;
     uint8_t* sKh = smem + 2 * TILE_BYTES;
     uint8_t* sKv = smem + 3 * TILE_BYTES;
+    __shared__ __align__(8) uint64_t tma_bar;
     __shared__ __align__(8) uint64_t mma_bar;
     __shared__ uint32_t tmem_base_slot;
     __shared__ uint32_t lut[8];   // thresholds by (v+4)/2; read as lut[(v+4)/2] = byte offset 2*v + 8
@@ -183,11 +210,8 @@ __global__ void __launch_bounds__(MMA_THREADS, 3) tc_update_mma_kernel(int8_t* _
     const int a = bi & 1, b = bj & 1, sx = bi >> 1, sy = bj >> 1;
     const long long sup = sup_offset(sx, sy, p.nbx);
     const long long base = sup + sub_offset(a, b);
-    const int8_t* gH = lat + sup + sub_offset(1 - a, b);
-    const int8_t* gV = lat + sup + sub_offset(a, 1 - b);
-    const int di = (a == 0) ? -1 : +1, dj = (b == 0) ? -1 : +1;
 
-    // ---- TMEM allocation (warp 0) and barrier init ------------------------------------------
+    // ---- TMEM allocation (warp 0), barriers, TMA of the four operand tiles (thread 0) -----------
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_addr(&tmem_base_slot)),
                      "r"((uint32_t)SUBN)
@@ -195,46 +219,37 @@ __global__ void __launch_bounds__(MMA_THREADS, 3) tc_update_mma_kernel(int8_t* _
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     if (t == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr(&tma_bar)));
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr(&mma_bar)));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(&tma_bar)),
+                     "r"((uint32_t)(4 * TILE_BYTES))
+                     : "memory");
+        // source sub-blocks: H = (1-a, b) holds the left/right neighbours, V = (a, 1-b) the up/down ones
+        tma_load_rows(sH, &lat_map, (int)((sup + sub_offset(1 - a, b)) >> 7), &tma_bar);
+        tma_load_rows(sV, &lat_map, (int)((sup + sub_offset(a, 1 - b)) >> 7), &tma_bar);
+        // bidiagonal matrices: Kh[n][k] = 1 for k = n, n + di (B operand, K-major); Kv[j][k] = 1 for
+        // k = j, j + dj (A operand); di = -1/+1 for a = 0/1, dj = -1/+1 for b = 0/1
+        tma_load_rows(sKh, &k_map, SUBN * a, &tma_bar);
+        tma_load_rows(sKv, &k_map, SUBN * (2 + b), &tma_bar);
     }
     if (t < 5) lut[t] = p.always[t] ? 0xffffffffu : p.thr[t];
-
-    // ---- operand tiles: coalesced 16-byte chunks of the two source sub-blocks ----------------
-#pragma unroll
-    for (int u = 0; u < 4; u++) {
-        const int q = t + MMA_THREADS * u, row = q >> 3, ch = q & 7;
-        *reinterpret_cast<uint4*>(sH + img(row, 16 * ch)) = *reinterpret_cast<const uint4*>(gH + row * SUBN + 16 * ch);
-        *reinterpret_cast<uint4*>(sV + img(row, 16 * ch)) = *reinterpret_cast<const uint4*>(gV + row * SUBN + 16 * ch);
-    }
-    // bidiagonal matrices: threads 0..127 write row t of Kh, threads 128..255 row t-128 of Kv.
-    // Kh is the B operand stored K-major: row = output column n, ones at k = n and k = n + di.
-    // Kv is the A operand: row = output row j, ones at k = j and k = j + dj.
-    {
-        uint8_t* K = (t < SUBN) ? sKh : sKv;
-        const int row = t & (SUBN - 1), d = (t < SUBN) ? di : dj;
-        const uint4 z = make_uint4(0, 0, 0, 0);
-#pragma unroll
-        for (int ch = 0; ch < 8; ch++) *reinterpret_cast<uint4*>(K + img(row, 16 * ch)) = z;
-        __syncwarp();
-        K[img(row, row)] = 1;
-        if (row + d >= 0 && row + d < SUBN) K[img(row, row + d)] = 1;
-    }
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> UMMA (async proxy)
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_d = tmem_base_slot;
 
-    // ---- 8 MMAs issued by one thread, completion signalled on the mbarrier --------------------
+    // ---- 8 MMAs issued by one thread once the tiles have landed ------------------------------
     if (t == 0) {
+        mbar_wait_parity0(&tma_bar);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t aH = smem_addr(sH), aV = smem_addr(sV), aKh = smem_addr(sKh), aKv = smem_addr(sKv);
 #pragma unroll
-        for (int s = 0; s < 4; s++)      // H (K-major A) x Kh (K-major B): k-step = 2 core matrices = 256 B
-            umma_i8(tmem_d, umma_desc(aH + 256 * s, 128, 1024), umma_desc(aKh + 256 * s, 128, 1024), IDESC_I8(0, 0), s > 0);
+        for (int s = 0; s < 4; s++)      // H (K-major A) x Kh (K-major B): k-step = 32 bytes inside the 128-byte rows
+            umma_i8(tmem_d, umma_desc_sw128(aH + 32 * s), umma_desc_sw128(aKh + 32 * s), IDESC_I8(0, 0), s > 0);
 #pragma unroll
-        for (int s = 0; s < 4; s++)      // Kv (K-major A) x V (MN-major B): k-step = 4 groups of 8 rows = 4096 B
-            umma_i8(tmem_d, umma_desc(aKv + 256 * s, 128, 1024), umma_desc(aV + 4096 * s, 1024, 128), IDESC_I8(0, 1), 1u);
+        for (int s = 0; s < 4; s++)      // Kv (K-major A) x V (MN-major B): k-step = 32 rows = 4096 bytes
+            umma_i8(tmem_d, umma_desc_sw128(aKv + 32 * s), umma_desc_sw128(aV + 4096 * s), IDESC_I8(0, 1), 1u);
         asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_addr(&mma_bar))
                      : "memory");
     }
@@ -261,16 +276,7 @@ __global__ void __launch_bounds__(MMA_THREADS, 3) tc_update_mma_kernel(int8_t* _
     const uint32_t lut_base = smem_addr(lut) + 8;
 
     // wait for the MMAs
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "W_%=:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n"
-        "@p bra D_%=;\n"
-        "bra W_%=;\n"
-        "D_%=:\n"
-        "}\n" ::"r"(smem_addr(&mma_bar))
-        : "memory");
+    mbar_wait_parity0(&mma_bar);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 
 #pragma unroll
@@ -414,6 +420,8 @@ struct ising_tc_ctx {
     TcParams base{};
     int8_t* lat = nullptr;
     int8_t* scratch = nullptr;
+    int8_t* kmat = nullptr;      // 4 x 128 x 128 bidiagonal 0/1 matrices: Kh(di=-1), Kh(di=+1), Kv(dj=-1), Kv(dj=+1)
+    CUtensorMap lat_map, k_map;
     long long* d_sum = nullptr;
     cudaStream_t stream = nullptr;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
@@ -441,6 +449,37 @@ static int tc_create_impl(int nbx, int nby, uint64_t seed, float alpha, int devi
         (e = cudaEventCreate(&c->e0)) != cudaSuccess || (e = cudaEventCreate(&c->e1)) != cudaSuccess) {
         ising_tc_destroy(c);
         return tc_fail(ISING_ECUDA, "tensor-core context: %s", cudaGetErrorString(e));
+    }
+    // constant bidiagonal matrices + TMA maps (128-byte rows, 128 x 128 boxes, 128-byte swizzle)
+    {
+        std::vector<int8_t> k(4 * SUBN * SUBN, 0);
+        for (int m = 0; m < 4; m++) {
+            const int d = (m & 1) ? +1 : -1;
+            for (int r = 0; r < SUBN; r++) {
+                k[(size_t)m * SUBN * SUBN + r * SUBN + r] = 1;
+                if (r + d >= 0 && r + d < SUBN) k[(size_t)m * SUBN * SUBN + r * SUBN + r + d] = 1;
+            }
+        }
+        TC_TRY(cudaMalloc(&c->kmat, k.size()));
+        TC_TRY(cudaMemcpy(c->kmat, k.data(), k.size(), cudaMemcpyHostToDevice));
+        typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                     const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                     CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+        void* fp = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fp, cudaEnableDefault, &q) != cudaSuccess || !fp)
+            return tc_fail(ISING_ECUDA, "cuTensorMapEncodeTiled entry point unavailable");
+        EncodeFn enc = (EncodeFn)fp;
+        const cuuint32_t box[2] = {SUBN, SUBN}, estr[2] = {1, 1};
+        const cuuint64_t strides[1] = {SUBN};
+        const cuuint64_t dl[2] = {SUBN, (cuuint64_t)(c->n / SUBN)}, dk[2] = {SUBN, 4 * SUBN};
+        CUresult r1 = enc(&c->lat_map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, c->lat, dl, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        CUresult r2 = enc(&c->k_map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, c->kmat, dk, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r1 != CUDA_SUCCESS || r2 != CUDA_SUCCESS) return tc_fail(ISING_ECUDA, "cuTensorMapEncodeTiled failed (%d, %d)", (int)r1, (int)r2);
     }
     // acceptance values with the device expf, then exact integer thresholds
     float* d_acc = nullptr;
@@ -471,7 +510,7 @@ static int tc_launch_color(ising_tc_ctx* c, bool black, uint64_t iter, int8_t* n
     p.call0 = (2ull * iter + (black ? 0 : 1)) * 4ull;   // offset (2*iter [+1])*16 draws, main.cu:269/:294
     const int ctas = 2 * c->nbx * c->nby;
     if (c->nn_path == ISING_TC_NN_MMA) {
-        const size_t smem = 4 * TILE_BYTES;
+        const size_t smem = 4 * TILE_BYTES + 1024;
         static bool attr_set = false;
         if (!attr_set) {
             TC_TRY(cudaFuncSetAttribute(tc_update_mma_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -480,9 +519,9 @@ static int tc_launch_color(ising_tc_ctx* c, bool black, uint64_t iter, int8_t* n
             attr_set = true;
         }
         p.st = make_step_tables_at(c->seed, p.call0);
-        if (nn_out)       tc_update_mma_kernel<true, false><<<ctas, MMA_THREADS, smem, c->stream>>>(c->lat, nn_out, p);
-        else if (p.fast)  tc_update_mma_kernel<false, true><<<ctas, MMA_THREADS, smem, c->stream>>>(c->lat, nullptr, p);
-        else              tc_update_mma_kernel<false, false><<<ctas, MMA_THREADS, smem, c->stream>>>(c->lat, nullptr, p);
+        if (nn_out)       tc_update_mma_kernel<true, false><<<ctas, MMA_THREADS, smem, c->stream>>>(c->lat_map, c->k_map, c->lat, nn_out, p);
+        else if (p.fast)  tc_update_mma_kernel<false, true><<<ctas, MMA_THREADS, smem, c->stream>>>(c->lat_map, c->k_map, c->lat, nullptr, p);
+        else              tc_update_mma_kernel<false, false><<<ctas, MMA_THREADS, smem, c->stream>>>(c->lat_map, c->k_map, c->lat, nullptr, p);
     } else {
         if (nn_out) tc_update_stencil_kernel<true><<<ctas, SUBN, 0, c->stream>>>(c->lat, nn_out, p);
         else        tc_update_stencil_kernel<false><<<ctas, SUBN, 0, c->stream>>>(c->lat, nullptr, p);
@@ -505,6 +544,7 @@ int ising_tc_destroy(ising_tc_ctx* c)
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->lat) cudaFree(c->lat);
+    if (c->kmat) cudaFree(c->kmat);
     if (c->scratch) cudaFree(c->scratch);
     if (c->d_sum) cudaFree(c->d_sum);
     if (c->e0) cudaEventDestroy(c->e0);
