@@ -165,6 +165,7 @@ int launch_part(ising_ctx* c, int dev, int color, int it, int part, cudaStream_t
         p.tile_row0 = 1; gy = tiles_y - 2;
         if (gy <= 0) return ISING_OK;
     }
+    p.launch_tile_rows = gy;
     if (c->fused) {
         if (part != ISING_PART_ALL) return fail(ISING_ESTATE, "edge/interior parts are not used with the fused halo push");
         const int Y = c->cfg.Y;

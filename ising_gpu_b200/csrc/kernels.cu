@@ -279,10 +279,13 @@ update_color_kernel(const __grid_constant__ CUtensorMap src_tile, const __grid_c
     __shared__ alignas(128) uint32_t sR[TH * SIDE_W];
     __shared__ alignas(8) uint64_t bar;
 
+    // tile-row index of this CTA: (y, z) of the grid, because gridDim.y alone stops at 65535
+    const int by = (int)(blockIdx.z * gridDim.y + blockIdx.y);
+    if (by >= p.launch_tile_rows) return;
     int tile_row;
-    if (p.edges_mode) tile_row = (blockIdx.y == 0) ? p.tile_row0 : p.tile_row_alt;
-    else if (PUSH)    tile_row = (blockIdx.y == 0) ? 0 : ((blockIdx.y == 1) ? (int)gridDim.y - 1 : (int)blockIdx.y - 1);
-    else              tile_row = p.tile_row0 + (int)blockIdx.y;
+    if (p.edges_mode) tile_row = (by == 0) ? p.tile_row0 : p.tile_row_alt;
+    else if (PUSH)    tile_row = (by == 0) ? 0 : ((by == 1) ? p.launch_tile_rows - 1 : by - 1);
+    else              tile_row = p.tile_row0 + by;
     const int x0 = blockIdx.x * TW;       // first word of the tile in the row
     const int y0 = tile_row * TH;         // first local row of the tile
     const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
@@ -387,11 +390,18 @@ update_color_kernel(const __grid_constant__ CUtensorMap src_tile, const __grid_c
     }
 }
 
+// (tiles_x, tile rows) as a 3-D grid: rows beyond 32768 spill into z
+static dim3 tile_grid(int tiles_x, int tile_rows)
+{
+    const int gy = tile_rows < 32768 ? tile_rows : 32768;
+    return dim3((unsigned)tiles_x, (unsigned)gy, (unsigned)((tile_rows + gy - 1) / gy));
+}
+
 void launch_update(const CUtensorMap& src_tile, const CUtensorMap& src_row, const CUtensorMap& src_side,
                    uint32_t* dst, const uint32_t* bonds, const UpdateParams& p, int tiles_x, int tiles_y,
                    cudaStream_t stream)
 {
-    const dim3 grid((unsigned)tiles_x, (unsigned)tiles_y);
+    const dim3 grid = tile_grid(tiles_x, tiles_y);
 #define ISING_LAUNCH(F, B, P) \
     update_color_kernel<F, B, P><<<grid, UPDATE_THREADS, 0, stream>>>(src_tile, src_row, src_side, dst, bonds, p)
     const int sel = (p.rule.fast ? 4 : 0) | (bonds ? 2 : 0) | (p.push ? 1 : 0);
@@ -422,7 +432,9 @@ __global__ void __launch_bounds__(UPDATE_THREADS) init_kernel(uint32_t* __restri
 {
     const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
     const int x0 = blockIdx.x * TW;
-    const int row = blockIdx.y * TH + ty;
+    const int by = (int)(blockIdx.z * gridDim.y + blockIdx.y);
+    if (by >= p.rows / TH) return;
+    const int row = by * TH + ty;
     const uint32_t grow = p.grow0 + (uint32_t)row;
     const uint32_t tid = ref_tid(grow, (uint32_t)(x0 + tx), p.grid_x);
     const ThreadConsts tc = make_thread_consts(tid, p.st.x1, p.st.k1r3);
@@ -436,8 +448,7 @@ __global__ void __launch_bounds__(UPDATE_THREADS) init_kernel(uint32_t* __restri
 
 void launch_init(uint32_t* plane, const InitParams& p, cudaStream_t stream)
 {
-    const dim3 grid((unsigned)(p.pitch / TW), (unsigned)(p.rows / TH));
-    init_kernel<<<grid, UPDATE_THREADS, 0, stream>>>(plane, p);
+    init_kernel<<<tile_grid(p.pitch / TW, p.rows / TH), UPDATE_THREADS, 0, stream>>>(plane, p);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -530,7 +541,7 @@ __global__ void __launch_bounds__(UPDATE_THREADS) bond_random_kernel(uint32_t* _
 {
     const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
     const int x0 = blockIdx.x * TW;
-    const int arow = blockIdx.y * TH + ty;            // allocation row 0 .. Y+1
+    const int arow = (int)(blockIdx.z * gridDim.y + blockIdx.y) * TH + ty;   // allocation row 0 .. Y+1
     if (arow >= p.rows + 2) return;
     // global row of allocation row arow (local row arow-1), periodic over the whole lattice
     const long long g = ((long long)p.grow0 + arow - 1 + p.total_rows) % p.total_rows;
@@ -601,8 +612,7 @@ __global__ void __launch_bounds__(256) bond_mirror_kernel(const uint32_t* __rest
 
 void launch_bond_init(uint32_t* random_planes, uint32_t* mirror_planes, const BondParams& p, cudaStream_t stream)
 {
-    const dim3 grid((unsigned)(p.pitch / TW), (unsigned)((p.rows + 2 + TH - 1) / TH));
-    bond_random_kernel<<<grid, UPDATE_THREADS, 0, stream>>>(random_planes, p);
+    bond_random_kernel<<<tile_grid(p.pitch / TW, (p.rows + 2 + TH - 1) / TH), UPDATE_THREADS, 0, stream>>>(random_planes, p);
     bond_mirror_kernel<<<148 * 8, 256, 0, stream>>>(random_planes, mirror_planes, p);
 }
 
@@ -665,7 +675,9 @@ __global__ void __launch_bounds__(128) corr_kernel(const __grid_constant__ CorrP
 
 void launch_corr(const CorrParams& p, unsigned long long* equal, cudaStream_t stream)
 {
-    corr_kernel<<<p.rows, 128, 2 * (size_t)p.pitch * sizeof(uint32_t), stream>>>(p, equal);
+    const size_t smem = 2 * (size_t)p.pitch * sizeof(uint32_t);
+    if (smem > 48 * 1024) cudaFuncSetAttribute(corr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    corr_kernel<<<p.rows, 128, smem, stream>>>(p, equal);
 }
 
 // ------------------------------------------------------------------------------------------

@@ -33,6 +33,7 @@ struct UpdateParams {
     int tile_row0;          // first tile row handled by blockIdx.y == 0
     int tile_row_alt;       // edges mode: tile row handled by blockIdx.y == 1
     int edges_mode;
+    int launch_tile_rows;   // tile rows covered by this launch (grid y*z may overshoot)
     int rows;               // local rows Y
     int pitch;              // words per row
     int yperiod;            // vertical wrap period in rows inside the slab; 0 = ghost rows

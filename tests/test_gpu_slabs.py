@@ -103,3 +103,46 @@ def test_one_process_per_gpu_nccl(oracle, tmp_path, overlap):
     gb = np.vstack([np.load(out / ("b%d.npy" % k)) for k in range(2)])
     gw = np.vstack([np.load(out / ("w%d.npy" % k)) for k in range(2)])
     assert np.array_equal(gb, ob) and np.array_equal(gw, ow)
+
+
+def test_more_than_65535_tile_rows(ig):
+    """1 120 000 rows = 70 000 tile rows (beyond gridDim.y): one tall context == two stacked slabs."""
+    import torch
+    from ising_gpu_b200.engine import F_NO_PEER_COPY, PART_ALL
+    from ising_gpu_b200.slab import _DevRows
+    X, Y2 = 2048, 560000
+    dev = torch.device("cuda", 0)
+    with ig.IsingEngine(X, 2 * Y2, temp=TC) as tall:
+        tall.init_lattice()
+        tall.sweeps(2)
+        tb, tw = tall.export_bits()
+        cnt = tall.count_spins()
+    engs = [ig.IsingEngine(X, Y2, temp=TC, slab_first=s, slab_count=2, flags=F_NO_PEER_COPY) for s in range(2)]
+
+    def row(e, color, r):
+        p, n = e.row_ptr(0, color, r)
+        return torch.as_tensor(_DevRows(p, n), device=dev)
+
+    def exchange(color):
+        for e in engs:
+            e.sync()
+        for s, e in enumerate(engs):
+            o = engs[1 - s]
+            row(o, color, Y2).copy_(row(e, color, 0))
+            row(o, color, -1).copy_(row(e, color, Y2 - 1))
+        torch.cuda.synchronize()
+
+    for e in engs:
+        e.init_lattice()
+    exchange(0); exchange(1)
+    for it in (1, 2):
+        for color in (0, 1):
+            for e in engs:
+                e.update_color_part(0, color, it, PART_ALL)
+            exchange(color)
+    gb = np.vstack([e.export_bits()[0] for e in engs])
+    gw = np.vstack([e.export_bits()[1] for e in engs])
+    assert np.array_equal(gb, tb) and np.array_equal(gw, tw)
+    assert sum(e.count_spins()[0] for e in engs) == cnt[0]
+    for e in engs:
+        e.close()
