@@ -166,8 +166,7 @@ int launch_part(ising_ctx* c, int dev, int color, int it, int part, cudaStream_t
         if (gy <= 0) return ISING_OK;
     }
     p.launch_tile_rows = gy;
-    if (c->fused) {
-        if (part != ISING_PART_ALL) return fail(ISING_ESTATE, "edge/interior parts are not used with the fused halo push");
+    if (c->fused && part != ISING_PART_INTERIOR) {   // the launch that owns the edge rows pushes them
         const int Y = c->cfg.Y;
         p.push = 1;
         p.push_up = d.up_plane[color] + (size_t)(Y + 1) * c->pitch;   // neighbour above: its bottom ghost row
@@ -526,9 +525,21 @@ int ising_export_bonds_ref_layout(ising_ctx* c, int dev, uint64_t* random, uint6
 int ising_update_color(ising_ctx* c, int color, int it)
 {
     if (!c || (color != 0 && color != 1)) return fail(ISING_EINVAL, "bad argument");
+    if (c->fused) {
+        // edge tile rows first, in the kernel variant that stores them into the neighbours' ghost
+        // rows; the interior follows on the same stream in the plain variant (measured 1-2 % faster
+        // per launch than one kernel carrying the push code for every CTA)
+        const bool split = c->cfg.Y / TH > 2;
+        for (int i = 0; i < (int)c->dev.size(); i++) {
+            if (int rc = launch_part(c, i, color, it, split ? ISING_PART_EDGES : ISING_PART_ALL, c->dev[i].stream)) return rc;
+            if (split)
+                if (int rc = launch_part(c, i, color, it, ISING_PART_INTERIOR, c->dev[i].stream)) return rc;
+        }
+        c->pushes_done[color]++;
+        return ISING_OK;
+    }
     for (int i = 0; i < (int)c->dev.size(); i++)
         if (int rc = launch_part(c, i, color, it, ISING_PART_ALL, c->dev[i].stream)) return rc;
-    if (c->fused) { c->pushes_done[color]++; return ISING_OK; }
     if (c->peer_halo) return push_halo(c, color);
     return ISING_OK;
 }
