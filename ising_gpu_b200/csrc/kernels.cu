@@ -47,19 +47,6 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, i
         "l"(map), "r"(x), "r"(y), "r"(smem_u32(bar))
         : "memory");
 }
-__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, int x, int y, const void* src)
-{
-    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(map), "r"(x),
-                 "r"(y), "r"(smem_u32(src))
-                 : "memory");
-}
-__device__ __forceinline__ void tma_store_commit_wait()
-{
-    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-}
-__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-
 __device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int* p)
 {
     unsigned int v;
