@@ -216,6 +216,10 @@ enum { ISING_TC_NN_MMA = 0,     /* INT8 tensor-core contraction (product path)  
 /* nbx, nby: lattice columns / rows in units of 256 (-x, -y of ising_tensorcore, main.cu:402-451);
  * alpha: temperature in T_crit units (-a); seed (-s, default 1234). */
 int ising_tc_create(int nbx, int nby, uint64_t seed, float alpha, int device, ising_tc_ctx** out);
+/* -g NGPUS (main.cu:447-451): the super-block rows are split over ngpus devices of this process
+ * (nby % ngpus == 0), each device updates its slab and reads the neighbouring slabs' edge rows
+ * through peer access; devices first_device .. first_device+ngpus-1. */
+int ising_tc_create_multi(int nbx, int nby, uint64_t seed, float alpha, int first_device, int ngpus, ising_tc_ctx** out);
 int ising_tc_destroy(ising_tc_ctx* ctx);
 int ising_tc_set_nn_path(ising_tc_ctx* ctx, int path);
 /* init_spins (main.cu:492-497) */

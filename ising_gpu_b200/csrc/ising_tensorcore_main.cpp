@@ -85,14 +85,10 @@ int main(int argc, char** argv)
         fprintf(stderr, "ERROR: Number of super blocks in y dimension must be multiple of number of gpus.\n");
         exit(EXIT_FAILURE);
     }
-    if (nGPUs != 1) {
-        fprintf(stderr, "ERROR: this build of the tensor-core variant drives one GPU (-g 1); see DESIGN.md.\n");
-        exit(EXIT_FAILURE);
-    }
     const long long nx = (long long)nbx * 256, ny = (long long)nby * 256;
 
     ising_tc_ctx* ctx = nullptr;
-    TC_CALL(ising_tc_create(nbx, nby, seed, alpha, 0, &ctx));
+    TC_CALL(ising_tc_create_multi(nbx, nby, seed, alpha, 0, nGPUs, &ctx));
     TC_CALL(ising_tc_init(ctx));
     TC_CALL(ising_tc_sync(ctx));
 

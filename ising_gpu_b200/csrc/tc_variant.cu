@@ -35,8 +35,13 @@ constexpr int SUPN = 256;   // LATTICE_SUP_N
 constexpr int SUBN = 128;   // LATTICE_SUB_N
 constexpr int TPS = SUBN * SUBN / 16;   // reference threads per sub-block (NLOOPS*SPINSPERTHREAD = 16)
 
+constexpr int MAX_TC_SLABS = 16;
+
 struct TcParams {
-    int nbx, nby;
+    int nbx, nby;            // super-blocks of the WHOLE lattice
+    int nby_loc;             // super-block rows per device (slab), nby / ngpus (main.cu:243, :266 split by batch)
+    int slab;                // this launch's slab; it owns super-block rows [slab*nby_loc, (slab+1)*nby_loc)
+    int8_t* slab_base[MAX_TC_SLABS];   // storage of every slab (peer-mapped), for the terms that cross a slab edge
     uint32_t key0, key1;
     uint64_t call0;          // Philox counter of the first of the 4 calls: 4*(2*iter + colour)
     uint32_t thr[5];         // accept iff x <= thr[k], k = (nn*s+4)/2 ...
@@ -53,16 +58,17 @@ __host__ __device__ __forceinline__ long long sup_offset(long long i, long long 
 }
 __host__ __device__ __forceinline__ long long sub_offset(int a, int b) { return ((long long)b * SUPN + (long long)a * SUBN) * SUBN; }
 
-// spin of sub-block kind (a,b) at element (i,j) of super-block (sx,sy), with i/j allowed to step
-// one element outside [0,128): continues in the periodic neighbour super-block.
-__device__ __forceinline__ int spin_at(const int8_t* __restrict__ lat, int nbx, int nby, int sx, int sy, int a, int b,
-                                       int i, int j)
+// spin of sub-block kind (a,b) at element (i,j) of super-block (sx,sy) of the whole lattice, with
+// i/j allowed to step one element outside [0,128): continues in the periodic neighbour
+// super-block, which may live on another device's slab.
+__device__ __forceinline__ int spin_at(const TcParams& p, int sx, int sy, int a, int b, int i, int j)
 {
-    if (i < 0) { i += SUBN; sx = (sx == 0) ? nbx - 1 : sx - 1; }
-    if (i >= SUBN) { i -= SUBN; sx = (sx == nbx - 1) ? 0 : sx + 1; }
-    if (j < 0) { j += SUBN; sy = (sy == 0) ? nby - 1 : sy - 1; }
-    if (j >= SUBN) { j -= SUBN; sy = (sy == nby - 1) ? 0 : sy + 1; }
-    return lat[sup_offset(sx, sy, nbx) + sub_offset(a, b) + (long long)j * SUBN + i];
+    if (i < 0) { i += SUBN; sx = (sx == 0) ? p.nbx - 1 : sx - 1; }
+    if (i >= SUBN) { i -= SUBN; sx = (sx == p.nbx - 1) ? 0 : sx + 1; }
+    if (j < 0) { j += SUBN; sy = (sy == 0) ? p.nby - 1 : sy - 1; }
+    if (j >= SUBN) { j -= SUBN; sy = (sy == p.nby - 1) ? 0 : sy + 1; }
+    const int d = sy / p.nby_loc;
+    return p.slab_base[d][sup_offset(sx, sy - d * p.nby_loc, p.nbx) + sub_offset(a, b) + (long long)j * SUBN + i];
 }
 
 // which sub-block does CTA `sb` of this colour own (update_spins :99-124)
@@ -80,11 +86,11 @@ template <bool WRITE_NN>
 __global__ void __launch_bounds__(SUBN) tc_update_stencil_kernel(int8_t* __restrict__ lat, int8_t* __restrict__ nn_out,
                                                                  const __grid_constant__ TcParams p)
 {
-    const int sb = blockIdx.x, j = threadIdx.x;
+    const int sb = blockIdx.x + p.slab * 2 * p.nbx * p.nby_loc, j = threadIdx.x;   // global sub-block index
     int bi, bj;
     block_of(sb, p.nbx, p.is_black != 0, bi, bj);
     const int a = bi & 1, b = bj & 1, sx = bi >> 1, sy = bj >> 1;
-    const long long base = sup_offset(sx, sy, p.nbx) + sub_offset(a, b);
+    const long long base = sup_offset(sx, sy - p.slab * p.nby_loc, p.nbx) + sub_offset(a, b);   // inside this slab
     const int di = (a == 0) ? -1 : +1, dj = (b == 0) ? -1 : +1;
 
     for (int c = 0; c < 16; c++) {
@@ -101,8 +107,8 @@ __global__ void __launch_bounds__(SUBN) tc_update_stencil_kernel(int8_t* __restr
 #pragma unroll
         for (int m = 0; m < 8; m++) {
             const int i = 8 * c + m;
-            const int nn = spin_at(lat, p.nbx, p.nby, sx, sy, 1 - a, b, i, j) + spin_at(lat, p.nbx, p.nby, sx, sy, 1 - a, b, i + di, j) +
-                           spin_at(lat, p.nbx, p.nby, sx, sy, a, 1 - b, i, j) + spin_at(lat, p.nbx, p.nby, sx, sy, a, 1 - b, i, j + dj);
+            const int nn = spin_at(p, sx, sy, 1 - a, b, i, j) + spin_at(p, sx, sy, 1 - a, b, i + di, j) +
+                           spin_at(p, sx, sy, a, 1 - b, i, j) + spin_at(p, sx, sy, a, 1 - b, i, j + dj);
             if (WRITE_NN) {
                 nn_out[base + (long long)j * SUBN + i] = (int8_t)nn;
             } else {
@@ -204,11 +210,12 @@ tc_update_mma_kernel(const __grid_constant__ CUtensorMap lat_map, const __grid_c
     __shared__ uint32_t tmem_base_slot;
     __shared__ uint32_t lut[8];   // thresholds by (v+4)/2; read as lut[(v+4)/2] = byte offset 2*v + 8
 
-    const int sb = blockIdx.x, t = threadIdx.x, warp = t >> 5, lane = t & 31;
+    const int sb = blockIdx.x + p.slab * 2 * p.nbx * p.nby_loc;   // global sub-block index (RNG map)
+    const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
     int bi, bj;
     block_of(sb, p.nbx, p.is_black != 0, bi, bj);
     const int a = bi & 1, b = bj & 1, sx = bi >> 1, sy = bj >> 1;
-    const long long sup = sup_offset(sx, sy, p.nbx);
+    const long long sup = sup_offset(sx, sy - p.slab * p.nby_loc, p.nbx);   // inside this device's slab
     const long long base = sup + sub_offset(a, b);
 
     // ---- TMEM allocation (warp 0), barriers, TMA of the four operand tiles (thread 0) -----------
@@ -263,13 +270,15 @@ tc_update_mma_kernel(const __grid_constant__ CUtensorMap lat_map, const __grid_c
     // horizontal edge term: lands on column 0 (a == 0) or 127 (a == 1) of every row
     const int edge_col = (a == 0) ? 0 : SUBN - 1;
     int edge_h = 0;
-    if ((edge_col >> 6) == half) edge_h = spin_at(lat, p.nbx, p.nby, sx, sy, 1 - a, b, (a == 0) ? -1 : SUBN, j);
+    if ((edge_col >> 6) == half) edge_h = spin_at(p, sx, sy, 1 - a, b, (a == 0) ? -1 : SUBN, j);
     // vertical edge term: a whole row, only for the first (b == 0) or last (b == 1) row of the block
     const bool has_edge_v = (b == 0) ? (j == 0) : (j == SUBN - 1);
     const int8_t* edge_row = nullptr;
     if (has_edge_v) {
         const int sy2 = (b == 0) ? (sy == 0 ? p.nby - 1 : sy - 1) : (sy == p.nby - 1 ? 0 : sy + 1);
-        edge_row = lat + sup_offset(sx, sy2, p.nbx) + sub_offset(a, 1 - b) + ((b == 0) ? (SUBN - 1) * SUBN : 0);
+        const int d2 = sy2 / p.nby_loc;      // the row above/below may belong to the neighbouring device
+        edge_row = p.slab_base[d2] + sup_offset(sx, sy2 - d2 * p.nby_loc, p.nbx) + sub_offset(a, 1 - b) +
+                   ((b == 0) ? (SUBN - 1) * SUBN : 0);
     }
     const int n = j >> 6;                        // which of the reference thread's two runs this row is
     const uint32_t tid0 = (uint32_t)sb * TPS + (uint32_t)(16 * (j & 63));
@@ -360,12 +369,13 @@ tc_update_mma_kernel(const __grid_constant__ CUtensorMap lat_map, const __grid_c
 }
 
 // init_spins: element t <- first output of Philox(subsequence t, offset 0); uniform < 0.5 -> -1
-__global__ void __launch_bounds__(256) tc_init_kernel(int8_t* __restrict__ lat, long long n, uint32_t key0, uint32_t key1,
-                                                     uint32_t thr_half)
+__global__ void __launch_bounds__(256) tc_init_kernel(int8_t* __restrict__ lat, long long n, long long t0, uint32_t key0,
+                                                     uint32_t key1, uint32_t thr_half)
 {
     for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x) {
+        const unsigned long long g = (unsigned long long)(t0 + t);   // element index in the whole lattice
         uint32_t o[4];
-        philox4x32_10(0u, 0u, (uint32_t)t, (uint32_t)((unsigned long long)t >> 32), key0, key1, o);
+        philox4x32_10(0u, 0u, (uint32_t)g, (uint32_t)(g >> 32), key0, key1, o);
         lat[t] = (o[0] <= thr_half) ? -1 : 1;
     }
 }
@@ -412,19 +422,24 @@ int tc_fail(int code, const char* fmt, ...)
 // the error string is shared with the main API through this hook (ising_api.cu)
 extern "C" void ising_internal_set_error(const char* msg);
 
-struct ising_tc_ctx {
-    int nbx = 0, nby = 0, device = 0, nn_path = ISING_TC_NN_MMA;
-    long long n = 0;
-    uint64_t seed = 0;
-    float alpha = 0, accept[5];
-    TcParams base{};
-    int8_t* lat = nullptr;
+struct TcDev {
+    int device = 0;
+    int8_t* lat = nullptr;       // this device's slab: nbx x nby_loc super-blocks
     int8_t* scratch = nullptr;
     int8_t* kmat = nullptr;      // 4 x 128 x 128 bidiagonal 0/1 matrices: Kh(di=-1), Kh(di=+1), Kv(dj=-1), Kv(dj=+1)
     CUtensorMap lat_map, k_map;
     long long* d_sum = nullptr;
     cudaStream_t stream = nullptr;
-    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    cudaEvent_t e0 = nullptr, e1 = nullptr, ev_color = nullptr;
+};
+
+struct ising_tc_ctx {
+    int nbx = 0, nby = 0, ngpus = 1, nby_loc = 0, nn_path = ISING_TC_NN_MMA;
+    long long n = 0, n_loc = 0;
+    uint64_t seed = 0;
+    float alpha = 0, accept[5];
+    TcParams base{};
+    std::vector<TcDev> dev;
     uint64_t launches = 0;
 };
 
@@ -435,67 +450,95 @@ struct ising_tc_ctx {
         return rc__;                                       \
     } while (0)
 
-static int tc_create_impl(int nbx, int nby, uint64_t seed, float alpha, int device, ising_tc_ctx** out)
+static int tc_create_impl(int nbx, int nby, uint64_t seed, float alpha, int first_device, int ngpus, ising_tc_ctx** out)
 {
     if (!out || nbx <= 0 || nby <= 0) return tc_fail(ISING_EINVAL, "nbx and nby must be positive");
     *out = nullptr;
-    TC_TRY(cudaSetDevice(device));
+    if (ngpus < 1 || ngpus > MAX_TC_SLABS) return tc_fail(ISING_EINVAL, "ngpus must be 1..%d", MAX_TC_SLABS);
+    if (nby % ngpus) return tc_fail(ISING_EINVAL, "Number of super blocks in y dimension must be multiple of number of gpus.");
+    int avail = 0;
+    TC_TRY(cudaGetDeviceCount(&avail));
+    if (first_device < 0 || first_device + ngpus > avail) return tc_fail(ISING_EINVAL, "devices %d..%d requested, %d visible", first_device, first_device + ngpus - 1, avail);
     ising_tc_ctx* c = new ising_tc_ctx();
-    c->nbx = nbx; c->nby = nby; c->device = device; c->seed = seed; c->alpha = alpha;
+    c->nbx = nbx; c->nby = nby; c->ngpus = ngpus; c->nby_loc = nby / ngpus; c->seed = seed; c->alpha = alpha;
     c->n = (long long)nbx * nby * SUPN * SUPN;
-    cudaError_t e;
-    if ((e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess ||
-        (e = cudaMalloc(&c->lat, (size_t)c->n)) != cudaSuccess || (e = cudaMalloc(&c->d_sum, sizeof(long long))) != cudaSuccess ||
-        (e = cudaEventCreate(&c->e0)) != cudaSuccess || (e = cudaEventCreate(&c->e1)) != cudaSuccess) {
-        ising_tc_destroy(c);
-        return tc_fail(ISING_ECUDA, "tensor-core context: %s", cudaGetErrorString(e));
-    }
-    // constant bidiagonal matrices + TMA maps (128-byte rows, 128 x 128 boxes, 128-byte swizzle)
-    {
-        std::vector<int8_t> k(4 * SUBN * SUBN, 0);
-        for (int m = 0; m < 4; m++) {
-            const int d = (m & 1) ? +1 : -1;
-            for (int r = 0; r < SUBN; r++) {
-                k[(size_t)m * SUBN * SUBN + r * SUBN + r] = 1;
-                if (r + d >= 0 && r + d < SUBN) k[(size_t)m * SUBN * SUBN + r * SUBN + r + d] = 1;
-            }
+    c->n_loc = c->n / ngpus;
+    c->dev.resize(ngpus);
+    auto bail = [&](int rc) { ising_tc_destroy(c); return rc; };
+
+    typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    void* fp = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fp, cudaEnableDefault, &q) != cudaSuccess || !fp)
+        return bail(tc_fail(ISING_ECUDA, "cuTensorMapEncodeTiled entry point unavailable"));
+    EncodeFn enc = (EncodeFn)fp;
+
+    // constant bidiagonal matrices
+    std::vector<int8_t> k(4 * SUBN * SUBN, 0);
+    for (int m = 0; m < 4; m++) {
+        const int d = (m & 1) ? +1 : -1;
+        for (int r = 0; r < SUBN; r++) {
+            k[(size_t)m * SUBN * SUBN + r * SUBN + r] = 1;
+            if (r + d >= 0 && r + d < SUBN) k[(size_t)m * SUBN * SUBN + r * SUBN + r + d] = 1;
         }
-        TC_TRY(cudaMalloc(&c->kmat, k.size()));
-        TC_TRY(cudaMemcpy(c->kmat, k.data(), k.size(), cudaMemcpyHostToDevice));
-        typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                     const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                     CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-        void* fp = nullptr;
-        cudaDriverEntryPointQueryResult q;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fp, cudaEnableDefault, &q) != cudaSuccess || !fp)
-            return tc_fail(ISING_ECUDA, "cuTensorMapEncodeTiled entry point unavailable");
-        EncodeFn enc = (EncodeFn)fp;
+    }
+    for (int i = 0; i < ngpus; i++) {
+        TcDev& d = c->dev[i];
+        d.device = first_device + i;
+        cudaError_t e;
+        if ((e = cudaSetDevice(d.device)) != cudaSuccess) return bail(tc_fail(ISING_ECUDA, "cudaSetDevice: %s", cudaGetErrorString(e)));
+        for (int j = 0; j < ngpus; j++) {   // slab edges read the neighbouring device's rows directly
+            if (j == i) continue;
+            int ok = 0;
+            cudaDeviceCanAccessPeer(&ok, d.device, first_device + j);
+            if (!ok) return bail(tc_fail(ISING_ENOPEER, "no direct link between devices %d and %d", d.device, first_device + j));
+            e = cudaDeviceEnablePeerAccess(first_device + j, 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return bail(tc_fail(ISING_ECUDA, "peer access: %s", cudaGetErrorString(e)));
+            cudaGetLastError();
+        }
+        if ((e = cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking)) != cudaSuccess ||
+            (e = cudaMalloc(&d.lat, (size_t)c->n_loc)) != cudaSuccess || (e = cudaMalloc(&d.d_sum, sizeof(long long))) != cudaSuccess ||
+            (e = cudaMalloc(&d.kmat, k.size())) != cudaSuccess ||
+            (e = cudaMemcpy(d.kmat, k.data(), k.size(), cudaMemcpyHostToDevice)) != cudaSuccess ||
+            (e = cudaEventCreate(&d.e0)) != cudaSuccess || (e = cudaEventCreate(&d.e1)) != cudaSuccess ||
+            (e = cudaEventCreateWithFlags(&d.ev_color, cudaEventDisableTiming)) != cudaSuccess)
+            return bail(tc_fail(ISING_ECUDA, "tensor-core context: %s", cudaGetErrorString(e)));
+        // TMA maps: 128-byte rows, 128 x 128 boxes, 128-byte swizzle
         const cuuint32_t box[2] = {SUBN, SUBN}, estr[2] = {1, 1};
         const cuuint64_t strides[1] = {SUBN};
-        const cuuint64_t dl[2] = {SUBN, (cuuint64_t)(c->n / SUBN)}, dk[2] = {SUBN, 4 * SUBN};
-        CUresult r1 = enc(&c->lat_map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, c->lat, dl, strides, box, estr,
-                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        CUresult r2 = enc(&c->k_map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, c->kmat, dk, strides, box, estr,
-                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        if (r1 != CUDA_SUCCESS || r2 != CUDA_SUCCESS) return tc_fail(ISING_ECUDA, "cuTensorMapEncodeTiled failed (%d, %d)", (int)r1, (int)r2);
+        const cuuint64_t dl[2] = {SUBN, (cuuint64_t)(c->n_loc / SUBN)}, dk[2] = {SUBN, 4 * SUBN};
+        const CUresult r1 = enc(&d.lat_map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, d.lat, dl, strides, box, estr,
+                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        const CUresult r2 = enc(&d.k_map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, d.kmat, dk, strides, box, estr,
+                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r1 != CUDA_SUCCESS || r2 != CUDA_SUCCESS) return bail(tc_fail(ISING_ECUDA, "cuTensorMapEncodeTiled failed (%d, %d)", (int)r1, (int)r2));
+        c->base.slab_base[i] = d.lat;
     }
     // acceptance values with the device expf, then exact integer thresholds
-    float* d_acc = nullptr;
-    TC_TRY(cudaMalloc(&d_acc, 5 * sizeof(float)));
-    const float inv_temp = 1.0f / (alpha * ISING_CRIT_TEMP);   // tensorcore/main.cu:578
-    tc_accept_kernel<<<1, 32, 0, c->stream>>>(inv_temp, d_acc);
-    TC_TRY(cudaMemcpyAsync(c->accept, d_acc, 5 * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
-    TC_TRY(cudaStreamSynchronize(c->stream));
-    TC_TRY(cudaFree(d_acc));
-    c->base.nbx = nbx; c->base.nby = nby;
+    {
+        TcDev& d = c->dev[0];
+        cudaError_t e;
+        float* d_acc = nullptr;
+        if ((e = cudaSetDevice(d.device)) != cudaSuccess || (e = cudaMalloc(&d_acc, 5 * sizeof(float))) != cudaSuccess)
+            return bail(tc_fail(ISING_ECUDA, "%s", cudaGetErrorString(e)));
+        const float inv_temp = 1.0f / (alpha * ISING_CRIT_TEMP);   // tensorcore/main.cu:578
+        tc_accept_kernel<<<1, 32, 0, d.stream>>>(inv_temp, d_acc);
+        if ((e = cudaMemcpyAsync(c->accept, d_acc, 5 * sizeof(float), cudaMemcpyDeviceToHost, d.stream)) != cudaSuccess ||
+            (e = cudaStreamSynchronize(d.stream)) != cudaSuccess)
+            return bail(tc_fail(ISING_ECUDA, "%s", cudaGetErrorString(e)));
+        cudaFree(d_acc);
+    }
+    c->base.nbx = nbx; c->base.nby = nby; c->base.nby_loc = c->nby_loc;
     c->base.key0 = (uint32_t)seed; c->base.key1 = (uint32_t)(seed >> 32);
-    for (int k = 0; k < 5; k++) {
-        const uint64_t n = accept_count(c->accept[k], true);   // uniform < accept (strict, main.cu:138)
-        c->base.always[k] = (n == (1ull << 32)) ? 0xffffffffu : 0u;
-        c->base.never[k] = (n == 0) ? 0xffffffffu : 0u;
-        c->base.thr[k] = (n == 0) ? 0u : (uint32_t)(n - 1);
+    for (int kk = 0; kk < 5; kk++) {
+        const uint64_t n = accept_count(c->accept[kk], true);   // uniform < accept (strict, main.cu:138)
+        c->base.always[kk] = (n == (1ull << 32)) ? 0xffffffffu : 0u;
+        c->base.never[kk] = (n == 0) ? 0xffffffffu : 0u;
+        c->base.thr[kk] = (n == 0) ? 0u : (uint32_t)(n - 1);
     }
     // fast shape: v = -4, -2 always flip; v = 0, 2, 4 are plain thresholds (or "always")
     c->base.fast = (c->base.always[0] && c->base.always[1] && !c->base.never[2] && !c->base.never[3] && !c->base.never[4]) ? 1 : 0;
@@ -503,31 +546,46 @@ static int tc_create_impl(int nbx, int nby, uint64_t seed, float alpha, int devi
     return ISING_OK;
 }
 
-static int tc_launch_color(ising_tc_ctx* c, bool black, uint64_t iter, int8_t* nn_out)
+// One colour on every device.  A device may start only when its ring neighbours have finished the
+// previous colour (their edge rows are read directly); the reference synchronises all devices on
+// the host instead (sync(), main.cu:228-235, :272, :297).
+static int tc_launch_color(ising_tc_ctx* c, bool black, uint64_t iter, int8_t** nn_out)
 {
-    TcParams p = c->base;
-    p.is_black = black ? 1 : 0;
-    p.call0 = (2ull * iter + (black ? 0 : 1)) * 4ull;   // offset (2*iter [+1])*16 draws, main.cu:269/:294
-    const int ctas = 2 * c->nbx * c->nby;
-    if (c->nn_path == ISING_TC_NN_MMA) {
-        const size_t smem = 4 * TILE_BYTES + 1024;
-        static bool attr_set = false;
-        if (!attr_set) {
+    const int g = c->ngpus;
+    for (int i = 0; i < g; i++) {
+        TcDev& d = c->dev[i];
+        TC_TRY(cudaSetDevice(d.device));
+        if (g > 1) {
+            TC_TRY(cudaStreamWaitEvent(d.stream, c->dev[(i + g - 1) % g].ev_color, 0));
+            TC_TRY(cudaStreamWaitEvent(d.stream, c->dev[(i + 1) % g].ev_color, 0));
+        }
+        TcParams p = c->base;
+        p.slab = i;
+        p.is_black = black ? 1 : 0;
+        p.call0 = (2ull * iter + (black ? 0 : 1)) * 4ull;   // offset (2*iter [+1])*16 draws, main.cu:269/:294
+        const int ctas = 2 * c->nbx * c->nby_loc;
+        int8_t* nn = nn_out ? nn_out[i] : nullptr;
+        if (c->nn_path == ISING_TC_NN_MMA) {
+            const size_t smem = 4 * TILE_BYTES + 1024;
             TC_TRY(cudaFuncSetAttribute(tc_update_mma_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             TC_TRY(cudaFuncSetAttribute(tc_update_mma_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             TC_TRY(cudaFuncSetAttribute(tc_update_mma_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            attr_set = true;
+            p.st = make_step_tables_at(c->seed, p.call0);
+            if (nn)           tc_update_mma_kernel<true, false><<<ctas, MMA_THREADS, smem, d.stream>>>(d.lat_map, d.k_map, d.lat, nn, p);
+            else if (p.fast)  tc_update_mma_kernel<false, true><<<ctas, MMA_THREADS, smem, d.stream>>>(d.lat_map, d.k_map, d.lat, nullptr, p);
+            else              tc_update_mma_kernel<false, false><<<ctas, MMA_THREADS, smem, d.stream>>>(d.lat_map, d.k_map, d.lat, nullptr, p);
+        } else {
+            if (nn) tc_update_stencil_kernel<true><<<ctas, SUBN, 0, d.stream>>>(d.lat, nn, p);
+            else    tc_update_stencil_kernel<false><<<ctas, SUBN, 0, d.stream>>>(d.lat, nullptr, p);
         }
-        p.st = make_step_tables_at(c->seed, p.call0);
-        if (nn_out)       tc_update_mma_kernel<true, false><<<ctas, MMA_THREADS, smem, c->stream>>>(c->lat_map, c->k_map, c->lat, nn_out, p);
-        else if (p.fast)  tc_update_mma_kernel<false, true><<<ctas, MMA_THREADS, smem, c->stream>>>(c->lat_map, c->k_map, c->lat, nullptr, p);
-        else              tc_update_mma_kernel<false, false><<<ctas, MMA_THREADS, smem, c->stream>>>(c->lat_map, c->k_map, c->lat, nullptr, p);
-    } else {
-        if (nn_out) tc_update_stencil_kernel<true><<<ctas, SUBN, 0, c->stream>>>(c->lat, nn_out, p);
-        else        tc_update_stencil_kernel<false><<<ctas, SUBN, 0, c->stream>>>(c->lat, nullptr, p);
+        TC_TRY(cudaGetLastError());
+        c->launches++;
     }
-    TC_TRY(cudaGetLastError());
-    c->launches++;
+    if (g > 1)
+        for (int i = 0; i < g; i++) {
+            TC_TRY(cudaSetDevice(c->dev[i].device));
+            TC_TRY(cudaEventRecord(c->dev[i].ev_color, c->dev[i].stream));
+        }
     return ISING_OK;
 }
 
@@ -535,21 +593,29 @@ extern "C" {
 
 int ising_tc_create(int nbx, int nby, uint64_t seed, float alpha, int device, ising_tc_ctx** out)
 {
-    TC_RET(tc_create_impl(nbx, nby, seed, alpha, device, out));
+    TC_RET(tc_create_impl(nbx, nby, seed, alpha, device, 1, out));
+}
+
+int ising_tc_create_multi(int nbx, int nby, uint64_t seed, float alpha, int first_device, int ngpus, ising_tc_ctx** out)
+{
+    TC_RET(tc_create_impl(nbx, nby, seed, alpha, first_device, ngpus, out));
 }
 
 int ising_tc_destroy(ising_tc_ctx* c)
 {
     if (!c) return ISING_OK;
-    cudaSetDevice(c->device);
-    if (c->stream) cudaStreamSynchronize(c->stream);
-    if (c->lat) cudaFree(c->lat);
-    if (c->kmat) cudaFree(c->kmat);
-    if (c->scratch) cudaFree(c->scratch);
-    if (c->d_sum) cudaFree(c->d_sum);
-    if (c->e0) cudaEventDestroy(c->e0);
-    if (c->e1) cudaEventDestroy(c->e1);
-    if (c->stream) cudaStreamDestroy(c->stream);
+    for (TcDev& d : c->dev) {
+        cudaSetDevice(d.device);
+        if (d.stream) cudaStreamSynchronize(d.stream);
+        if (d.lat) cudaFree(d.lat);
+        if (d.kmat) cudaFree(d.kmat);
+        if (d.scratch) cudaFree(d.scratch);
+        if (d.d_sum) cudaFree(d.d_sum);
+        if (d.e0) cudaEventDestroy(d.e0);
+        if (d.e1) cudaEventDestroy(d.e1);
+        if (d.ev_color) cudaEventDestroy(d.ev_color);
+        if (d.stream) cudaStreamDestroy(d.stream);
+    }
     delete c;
     return ISING_OK;
 }
@@ -561,14 +627,26 @@ int ising_tc_set_nn_path(ising_tc_ctx* c, int path)
     return ISING_OK;
 }
 
+static int tc_sync_impl(ising_tc_ctx* c)
+{
+    for (TcDev& d : c->dev) {
+        TC_TRY(cudaSetDevice(d.device));
+        TC_TRY(cudaStreamSynchronize(d.stream));
+    }
+    return ISING_OK;
+}
+
 static int tc_init_impl(ising_tc_ctx* c)
 {
-    TC_TRY(cudaSetDevice(c->device));
     const uint32_t thr_half = (uint32_t)(accept_count(0.5f, true) - 1);
-    tc_init_kernel<<<148 * 8, 256, 0, c->stream>>>(c->lat, c->n, c->base.key0, c->base.key1, thr_half);
-    TC_TRY(cudaGetLastError());
-    c->launches++;
-    return ISING_OK;
+    for (int i = 0; i < c->ngpus; i++) {
+        TcDev& d = c->dev[i];
+        TC_TRY(cudaSetDevice(d.device));
+        tc_init_kernel<<<148 * 8, 256, 0, d.stream>>>(d.lat, c->n_loc, (long long)i * c->n_loc, c->base.key0, c->base.key1, thr_half);
+        TC_TRY(cudaGetLastError());
+        c->launches++;
+    }
+    return tc_sync_impl(c);   // every slab is complete before any device reads a neighbour's edge
 }
 int ising_tc_init(ising_tc_ctx* c)
 {
@@ -578,7 +656,6 @@ int ising_tc_init(ising_tc_ctx* c)
 
 static int tc_update_impl(ising_tc_ctx* c, uint64_t first_iter, int n)
 {
-    TC_TRY(cudaSetDevice(c->device));
     for (int k = 0; k < n; k++) {
         if (int rc = tc_launch_color(c, true, first_iter + k, nullptr)) return rc;
         if (int rc = tc_launch_color(c, false, first_iter + k, nullptr)) return rc;
@@ -593,13 +670,25 @@ int ising_tc_update(ising_tc_ctx* c, uint64_t first_iter, int n)
 
 static int tc_timed_impl(ising_tc_ctx* c, uint64_t first_iter, int n, float* ms)
 {
-    TC_TRY(cudaSetDevice(c->device));
-    TC_TRY(cudaStreamSynchronize(c->stream));
-    TC_TRY(cudaEventRecord(c->e0, c->stream));
+    if (int rc = tc_sync_impl(c)) return rc;
+    for (TcDev& d : c->dev) {
+        TC_TRY(cudaSetDevice(d.device));
+        TC_TRY(cudaEventRecord(d.e0, d.stream));
+    }
     if (int rc = tc_update_impl(c, first_iter, n)) return rc;
-    TC_TRY(cudaEventRecord(c->e1, c->stream));
-    TC_TRY(cudaEventSynchronize(c->e1));
-    TC_TRY(cudaEventElapsedTime(ms, c->e0, c->e1));
+    float worst = 0.f;
+    for (TcDev& d : c->dev) {
+        TC_TRY(cudaSetDevice(d.device));
+        TC_TRY(cudaEventRecord(d.e1, d.stream));
+    }
+    for (TcDev& d : c->dev) {
+        TC_TRY(cudaSetDevice(d.device));
+        TC_TRY(cudaEventSynchronize(d.e1));
+        float t = 0.f;
+        TC_TRY(cudaEventElapsedTime(&t, d.e0, d.e1));
+        if (t > worst) worst = t;
+    }
+    *ms = worst;
     return ISING_OK;
 }
 int ising_tc_update_timed(ising_tc_ctx* c, uint64_t first_iter, int n, float* ms)
@@ -608,12 +697,6 @@ int ising_tc_update_timed(ising_tc_ctx* c, uint64_t first_iter, int n, float* ms
     TC_RET(tc_timed_impl(c, first_iter, n, ms));
 }
 
-static int tc_sync_impl(ising_tc_ctx* c)
-{
-    TC_TRY(cudaSetDevice(c->device));
-    TC_TRY(cudaStreamSynchronize(c->stream));
-    return ISING_OK;
-}
 int ising_tc_sync(ising_tc_ctx* c)
 {
     if (!c) TC_RET(tc_fail(ISING_EINVAL, "null context"));
@@ -622,15 +705,22 @@ int ising_tc_sync(ising_tc_ctx* c)
 
 static int tc_sum_impl(ising_tc_ctx* c, int64_t* sum)
 {
-    TC_TRY(cudaSetDevice(c->device));
-    TC_TRY(cudaMemsetAsync(c->d_sum, 0, sizeof(long long), c->stream));
-    tc_sum_kernel<<<148 * 8, 256, 0, c->stream>>>(c->lat, c->n, c->d_sum);
-    TC_TRY(cudaGetLastError());
-    c->launches++;
-    long long h = 0;
-    TC_TRY(cudaMemcpyAsync(&h, c->d_sum, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
-    TC_TRY(cudaStreamSynchronize(c->stream));
-    *sum = h;
+    long long tot = 0;
+    for (TcDev& d : c->dev) {
+        TC_TRY(cudaSetDevice(d.device));
+        TC_TRY(cudaMemsetAsync(d.d_sum, 0, sizeof(long long), d.stream));
+        tc_sum_kernel<<<148 * 8, 256, 0, d.stream>>>(d.lat, c->n_loc, d.d_sum);
+        TC_TRY(cudaGetLastError());
+        c->launches++;
+    }
+    for (TcDev& d : c->dev) {
+        long long h = 0;
+        TC_TRY(cudaSetDevice(d.device));
+        TC_TRY(cudaMemcpyAsync(&h, d.d_sum, sizeof(h), cudaMemcpyDeviceToHost, d.stream));
+        TC_TRY(cudaStreamSynchronize(d.stream));
+        tot += h;
+    }
+    *sum = tot;
     return ISING_OK;
 }
 int ising_tc_sum(ising_tc_ctx* c, int64_t* sum)
@@ -641,11 +731,13 @@ int ising_tc_sum(ising_tc_ctx* c, int64_t* sum)
 
 static int tc_copy_impl(ising_tc_ctx* c, int8_t* out, const int8_t* in)
 {
-    TC_TRY(cudaSetDevice(c->device));
-    if (out) TC_TRY(cudaMemcpyAsync(out, c->lat, (size_t)c->n, cudaMemcpyDeviceToHost, c->stream));
-    if (in) TC_TRY(cudaMemcpyAsync(c->lat, in, (size_t)c->n, cudaMemcpyHostToDevice, c->stream));
-    TC_TRY(cudaStreamSynchronize(c->stream));
-    return ISING_OK;
+    for (int i = 0; i < c->ngpus; i++) {   // the slabs are consecutive pieces of the storage order
+        TcDev& d = c->dev[i];
+        TC_TRY(cudaSetDevice(d.device));
+        if (out) TC_TRY(cudaMemcpyAsync(out + (size_t)i * c->n_loc, d.lat, (size_t)c->n_loc, cudaMemcpyDeviceToHost, d.stream));
+        if (in) TC_TRY(cudaMemcpyAsync(d.lat, in + (size_t)i * c->n_loc, (size_t)c->n_loc, cudaMemcpyHostToDevice, d.stream));
+    }
+    return tc_sync_impl(c);
 }
 int ising_tc_export_storage(ising_tc_ctx* c, int8_t* out)
 {
@@ -710,13 +802,21 @@ int ising_tc_accept_table(ising_tc_ctx* c, float out[5])
 
 static int tc_nn_impl(ising_tc_ctx* c, int is_black, int8_t* out)
 {
-    TC_TRY(cudaSetDevice(c->device));
-    if (!c->scratch) TC_TRY(cudaMalloc(&c->scratch, (size_t)c->n));
-    TC_TRY(cudaMemsetAsync(c->scratch, 0, (size_t)c->n, c->stream));
-    if (int rc = tc_launch_color(c, is_black != 0, 0, c->scratch)) return rc;
-    TC_TRY(cudaMemcpyAsync(out, c->scratch, (size_t)c->n, cudaMemcpyDeviceToHost, c->stream));
-    TC_TRY(cudaStreamSynchronize(c->stream));
-    return ISING_OK;
+    int8_t* scr[MAX_TC_SLABS];
+    for (int i = 0; i < c->ngpus; i++) {
+        TcDev& d = c->dev[i];
+        TC_TRY(cudaSetDevice(d.device));
+        if (!d.scratch) TC_TRY(cudaMalloc(&d.scratch, (size_t)c->n_loc));
+        TC_TRY(cudaMemsetAsync(d.scratch, 0, (size_t)c->n_loc, d.stream));
+        scr[i] = d.scratch;
+    }
+    if (int rc = tc_launch_color(c, is_black != 0, 0, scr)) return rc;
+    for (int i = 0; i < c->ngpus; i++) {
+        TcDev& d = c->dev[i];
+        TC_TRY(cudaSetDevice(d.device));
+        TC_TRY(cudaMemcpyAsync(out + (size_t)i * c->n_loc, d.scratch, (size_t)c->n_loc, cudaMemcpyDeviceToHost, d.stream));
+    }
+    return tc_sync_impl(c);
 }
 int ising_tc_neighbour_sums(ising_tc_ctx* c, int is_black, int8_t* out)
 {

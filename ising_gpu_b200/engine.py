@@ -85,6 +85,7 @@ def load_library():
         "ising_site_random": ([C.c_uint64, C.c_int32, C.c_int, C.c_int, C.c_uint32, C.c_uint32, C.c_int, u32p], None),
         "ising_launch_count": ([vp], C.c_uint64),
         "ising_tc_create": ([C.c_int, C.c_int, C.c_uint64, C.c_float, C.c_int, C.POINTER(vp)], C.c_int),
+        "ising_tc_create_multi": ([C.c_int, C.c_int, C.c_uint64, C.c_float, C.c_int, C.c_int, C.POINTER(vp)], C.c_int),
         "ising_tc_destroy": ([vp], C.c_int),
         "ising_tc_set_nn_path": ([vp, C.c_int], C.c_int),
         "ising_tc_init": ([vp], C.c_int),
@@ -117,7 +118,7 @@ EXPORTED_SYMBOLS = ("ising_create ising_destroy ising_last_error ising_abi_versi
                     "ising_device_count ising_device_info ising_can_access_peer "
                     "ising_ipc_export ising_ipc_attach ising_push_edges "
                     "ising_accept_table ising_site_random ising_launch_count ising_kernel_name "
-                    "ising_tc_create ising_tc_destroy ising_tc_set_nn_path ising_tc_init ising_tc_update "
+                    "ising_tc_create ising_tc_create_multi ising_tc_destroy ising_tc_set_nn_path ising_tc_init ising_tc_update "
                     "ising_tc_update_timed ising_tc_sync ising_tc_sum ising_tc_export_storage "
                     "ising_tc_import_storage ising_tc_export_true ising_tc_write_lattice ising_tc_accept_table "
                     "ising_tc_neighbour_sums ising_tc_launch_count").split()

@@ -12,14 +12,14 @@ NN_MMA, NN_STENCIL = 0, 1
 
 
 class TensorcoreEngine:
-    def __init__(self, nbx, nby, seed=1234, alpha=0.1, device=0, nn_path=None):
+    def __init__(self, nbx, nby, seed=1234, alpha=0.1, device=0, nn_path=None, ngpus=1):
         self._L = load_library()
         self.nbx, self.nby = int(nbx), int(nby)
         self.nx, self.ny = 256 * self.nbx, 256 * self.nby
         h = C.c_void_p()
         self._h = None
-        self._ck(self._L.ising_tc_create(self.nbx, self.nby, int(seed), C.c_float(float(np.float32(alpha))),
-                                         int(device), C.byref(h)))
+        self._ck(self._L.ising_tc_create_multi(self.nbx, self.nby, int(seed), C.c_float(float(np.float32(alpha))),
+                                               int(device), int(ngpus), C.byref(h)))
         self._h = h
         self.iter = 0
         if nn_path is not None:

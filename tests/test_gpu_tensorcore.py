@@ -50,3 +50,38 @@ def test_write_lattice_format(oracle, tmp_path):
     first = (tmp_path / "g.txt").read_text().split("\n")[0].split()
     assert len(first) == 256 and set(first) <= {"1", "-1"}
     eng.close()
+
+
+def _ngpus():
+    import torch
+    return torch.cuda.device_count()
+
+
+@pytest.mark.parametrize("nn_path", [0, 1])
+@pytest.mark.parametrize("nbx,nby,ngpus", [(2, 2, 2), (1, 4, 2), (3, 4, 4), (1, 8, 8)])
+def test_variant_multi_gpu_matches_oracle(oracle, nbx, nby, ngpus, nn_path):
+    """-g N (tensorcore/main.cu:240-298): super-block rows split over N devices; the global thread
+    ids keep the random numbers -- and therefore the lattice -- independent of N."""
+    if _ngpus() < ngpus:
+        pytest.skip("needs %d GPUs" % ngpus)
+    from ising_gpu_b200.tensorcore import TensorcoreEngine
+    eng = TensorcoreEngine(nbx, nby, seed=77, alpha=1.0, nn_path=nn_path, ngpus=ngpus)
+    ora = oracle.TensorcoreOracle(nbx, nby, seed=77, alpha=1.0)
+    ora.set_accept(eng.accept_table())
+    eng.init(); ora.init()
+    assert np.array_equal(eng.storage(), ora.storage())
+    for is_black in (1, 0):
+        assert np.array_equal(eng.neighbour_sums(is_black), ora.neighbour_sums(is_black))
+    for it in range(5):
+        eng.update(1); ora.update(1)
+        assert np.array_equal(eng.storage(), ora.storage()), "iteration %d" % (it + 1)
+    assert eng.sum() == ora.sum()
+    eng.close()
+
+
+def test_variant_multi_gpu_rejects_uneven_split():
+    from ising_gpu_b200.tensorcore import TensorcoreEngine
+    if _ngpus() < 2:
+        pytest.skip("needs 2 GPUs")
+    with pytest.raises(Exception):
+        TensorcoreEngine(1, 3, ngpus=2)
