@@ -132,9 +132,11 @@ __global__ void __launch_bounds__(SUBN) tc_update_stencil_kernel(int8_t* __restr
 // diagonal + the sub- or super-diagonal, by the parity (a,b) of the target sub-block): the
 // reference's "lat x K + K^T x lat" (tensorcore/main.cu:547-569) with int8 instead of fp16.
 // Eight tcgen05.mma.kind::i8 (M=128, N=128, K=32) accumulate into one 128-lane x 128-column
-// TMEM tile; H, Kh, Kv are K-major operands, V is used in place as an MN-major B operand (no
-// transposed copy).  All four tiles sit in shared memory in the no-swizzle canonical layout:
-// 8-row x 16-byte core matrices, image(row, byte) below.  The terms that cross the sub-block edge
+// TMEM tile; H is a K-major A operand, V is used in place as an MN-major B operand (no transposed
+// copy), and ONE bidiagonal matrix serves as Kh and Kv in all four parities: K-major for the
+// "+1" neighbour, MN-major (its transpose) for the "-1" neighbour.  H, V, K and the tile being
+// updated are brought by TMA with the 128-byte swizzle; the updated tile goes back with one TMA
+// store, so global memory only sees full 128-byte lines.  The terms that cross the sub-block edge
 // (add_boundaries, main.cu:148-226) are added in the epilogue from the neighbouring blocks.
 // Thread j owns TMEM lane j = row j of the sub-block: tcgen05.ld brings its 128 sums to
 // registers, where the 16 runs of 8 spins are updated with the reference's RNG map.
@@ -203,8 +205,9 @@ tc_update_mma_kernel(const __grid_constant__ CUtensorMap lat_map, const __grid_c
     uint8_t* smem = smem_raw + ((1024u - (smem_addr(smem_raw) & 1023u)) & 1023u);
     uint8_t* sH = smem;
     uint8_t* sV = smem + TILE_BYTES;
-    uint8_t* sKh = smem + 2 * TILE_BYTES;
-    uint8_t* sKv = smem + 3 * TILE_BYTES;
+    uint8_t* sK = smem + 2 * TILE_BYTES;
+    uint8_t* sOwn = smem + 3 * TILE_BYTES;
+    __shared__ __align__(16) int8_t sEdge[SUBN];   // the row across the vertical sub-block edge
     __shared__ __align__(8) uint64_t tma_bar;
     __shared__ __align__(8) uint64_t mma_bar;
     __shared__ uint32_t tmem_base_slot;
@@ -230,15 +233,28 @@ tc_update_mma_kernel(const __grid_constant__ CUtensorMap lat_map, const __grid_c
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr(&mma_bar)));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(&tma_bar)),
-                     "r"((uint32_t)(4 * TILE_BYTES))
+                     "r"((uint32_t)(4 * TILE_BYTES + SUBN))
                      : "memory");
         // source sub-blocks: H = (1-a, b) holds the left/right neighbours, V = (a, 1-b) the up/down ones
         tma_load_rows(sH, &lat_map, (int)((sup + sub_offset(1 - a, b)) >> 7), &tma_bar);
         tma_load_rows(sV, &lat_map, (int)((sup + sub_offset(a, 1 - b)) >> 7), &tma_bar);
-        // bidiagonal matrices: Kh[n][k] = 1 for k = n, n + di (B operand, K-major); Kv[j][k] = 1 for
-        // k = j, j + dj (A operand); di = -1/+1 for a = 0/1, dj = -1/+1 for b = 0/1
-        tma_load_rows(sKh, &k_map, SUBN * a, &tma_bar);
-        tma_load_rows(sKv, &k_map, SUBN * (2 + b), &tma_bar);
+        // one bidiagonal matrix K+[r][c] = 1 for c = r, r + 1 serves all four cases: taken K-major it is
+        // the "+1" operand, taken MN-major (transposed) the "-1" operand
+        tma_load_rows(sK, &k_map, SUBN, &tma_bar);
+        // the spins being updated: staged here, updated in place, stored back as one tile
+        tma_load_rows(sOwn, &lat_map, (int)(base >> 7), &tma_bar);
+        // vertical edge term (add_boundaries): last/first row of sub-block (a, 1-b) of the super-block
+        // above (b == 0) or below (b == 1), which may live in the neighbouring device's slab
+        {
+            const int sy2 = (b == 0) ? (sy == 0 ? p.nby - 1 : sy - 1) : (sy == p.nby - 1 ? 0 : sy + 1);
+            const int d2 = sy2 / p.nby_loc;
+            const int8_t* edge_row = p.slab_base[d2] + sup_offset(sx, sy2 - d2 * p.nby_loc, p.nbx) + sub_offset(a, 1 - b) +
+                                     ((b == 0) ? (SUBN - 1) * SUBN : 0);
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                             smem_addr(sEdge)),
+                         "l"(edge_row), "r"((uint32_t)SUBN), "r"(smem_addr(&tma_bar))
+                         : "memory");
+        }
     }
     if (t < 5) lut[t] = p.always[t] ? 0xffffffffu : p.thr[t];
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -250,13 +266,16 @@ tc_update_mma_kernel(const __grid_constant__ CUtensorMap lat_map, const __grid_c
     if (t == 0) {
         mbar_wait_parity0(&tma_bar);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t aH = smem_addr(sH), aV = smem_addr(sV), aKh = smem_addr(sKh), aKv = smem_addr(sKv);
+        const uint32_t aH = smem_addr(sH), aV = smem_addr(sV), aK = smem_addr(sK);
+        // k-step of a K-major operand = 32 bytes inside the 128-byte rows, of an MN-major one = 32 rows
+        const uint32_t kh_step = (a == 0) ? 4096u : 32u, kv_step = (b == 0) ? 4096u : 32u;
+        const uint32_t idesc_h = IDESC_I8(0, a == 0), idesc_v = IDESC_I8(b == 0, 1);
 #pragma unroll
-        for (int s = 0; s < 4; s++)      // H (K-major A) x Kh (K-major B): k-step = 32 bytes inside the 128-byte rows
-            umma_i8(tmem_d, umma_desc_sw128(aH + 32 * s), umma_desc_sw128(aKh + 32 * s), IDESC_I8(0, 0), s > 0);
+        for (int s = 0; s < 4; s++)      // H (K-major A) x Kh (B): nn[j][i] = H[j][i] + H[j][i+di]
+            umma_i8(tmem_d, umma_desc_sw128(aH + 32 * s), umma_desc_sw128(aK + kh_step * s), idesc_h, s > 0);
 #pragma unroll
-        for (int s = 0; s < 4; s++)      // Kv (K-major A) x V (MN-major B): k-step = 32 rows = 4096 bytes
-            umma_i8(tmem_d, umma_desc_sw128(aKv + 32 * s), umma_desc_sw128(aV + 4096 * s), IDESC_I8(0, 1), 1u);
+        for (int s = 0; s < 4; s++)      // Kv (A) x V (MN-major B, in place): += V[j][i] + V[j+dj][i]
+            umma_i8(tmem_d, umma_desc_sw128(aK + kv_step * s), umma_desc_sw128(aV + 4096 * s), idesc_v, 1u);
         asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_addr(&mma_bar))
                      : "memory");
     }
@@ -264,26 +283,23 @@ tc_update_mma_kernel(const __grid_constant__ CUtensorMap lat_map, const __grid_c
     // ---- while the tensor core works: own spins, edge terms ----------------------------------
     const int j = 32 * (warp & 3) + lane;        // row = TMEM lane
     const int half = warp >> 2;                  // columns 64*half .. 64*half+63
-    uint4 own[4];
-#pragma unroll
-    for (int ch = 0; ch < 4; ch++) own[ch] = *reinterpret_cast<const uint4*>(lat + base + j * SUBN + 64 * half + 16 * ch);
+    // own row in the swizzled tile: 16-byte chunk L of row j sits at chunk L ^ (j % 8)
+    uint4* own_row = reinterpret_cast<uint4*>(sOwn + j * SUBN);
+    const int swz = j & 7;
     // horizontal edge term: lands on column 0 (a == 0) or 127 (a == 1) of every row
     const int edge_col = (a == 0) ? 0 : SUBN - 1;
     int edge_h = 0;
     if ((edge_col >> 6) == half) edge_h = spin_at(p, sx, sy, 1 - a, b, (a == 0) ? -1 : SUBN, j);
     // vertical edge term: a whole row, only for the first (b == 0) or last (b == 1) row of the block
     const bool has_edge_v = (b == 0) ? (j == 0) : (j == SUBN - 1);
-    const int8_t* edge_row = nullptr;
-    if (has_edge_v) {
-        const int sy2 = (b == 0) ? (sy == 0 ? p.nby - 1 : sy - 1) : (sy == p.nby - 1 ? 0 : sy + 1);
-        const int d2 = sy2 / p.nby_loc;      // the row above/below may belong to the neighbouring device
-        edge_row = p.slab_base[d2] + sup_offset(sx, sy2 - d2 * p.nby_loc, p.nbx) + sub_offset(a, 1 - b) +
-                   ((b == 0) ? (SUBN - 1) * SUBN : 0);
-    }
     const int n = j >> 6;                        // which of the reference thread's two runs this row is
     const uint32_t tid0 = (uint32_t)sb * TPS + (uint32_t)(16 * (j & 63));
     const uint32_t lut_base = smem_addr(lut) + 8;
 
+    if (t != 0) mbar_wait_parity0(&tma_bar);   // own tile and edge row have landed (thread 0 waited above)
+    uint4 own[4];
+#pragma unroll
+    for (int ch = 0; ch < 4; ch++) own[ch] = own_row[(4 * half + ch) ^ swz];
     // wait for the MMAs
     mbar_wait_parity0(&mma_bar);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -309,12 +325,16 @@ tc_update_mma_kernel(const __grid_constant__ CUtensorMap lat_map, const __grid_c
         if (col0 == SUBN - 32 && edge_col == SUBN - 1) r[31] += (uint32_t)edge_h;
         if (has_edge_v) {
 #pragma unroll
-            for (int q = 0; q < 32; q++) r[q] += (uint32_t)(int)edge_row[col0 + q];
+            for (int q4 = 0; q4 < 8; q4++) {
+                const uint32_t e4 = *reinterpret_cast<const uint32_t*>(sEdge + col0 + 4 * q4);
+#pragma unroll
+                for (int q = 0; q < 4; q++) r[4 * q4 + q] += (uint32_t)(int)(int8_t)(e4 >> (8 * q));
+            }
         }
 #pragma unroll
         for (int cc = 0; cc < 4; cc++) {        // 4 runs of 8 spins per group
             const int c = (col0 >> 3) + cc;     // run index inside the row, 0..15
-            const uint4 w4 = own[2 * g + (cc >> 1)];
+            uint4& w4 = own[2 * g + (cc >> 1)];
             uint32_t w[2] = {(cc & 1) ? w4.z : w4.x, (cc & 1) ? w4.w : w4.y};   // 8 own spins, one per byte
             if (WRITE_NN) {
 #pragma unroll
@@ -356,14 +376,30 @@ tc_update_mma_kernel(const __grid_constant__ CUtensorMap lat_map, const __grid_c
                     }
                 }
             }
-            int8_t* dst = (WRITE_NN ? nn_out : lat) + base + j * SUBN + 8 * c;
-            *reinterpret_cast<uint2*>(dst) = make_uint2(w[0], w[1]);
+            if (WRITE_NN) {
+                *reinterpret_cast<uint2*>(nn_out + base + j * SUBN + 8 * c) = make_uint2(w[0], w[1]);
+            } else {
+                if (cc & 1) { w4.z = w[0]; w4.w = w[1]; }
+                else        { w4.x = w[0]; w4.y = w[1]; }
+            }
         }
     }
+    if (!WRITE_NN) {
+#pragma unroll
+        for (int ch = 0; ch < 4; ch++) own_row[(4 * half + ch) ^ swz] = own[ch];
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the TMA store
+    }
 
-    // ---- release TMEM -------------------------------------------------------------------------
+    // ---- store the tile, release TMEM -----------------------------------------------------------
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    if (!WRITE_NN && t == 0) {
+        asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(&lat_map), "r"(0),
+                     "r"((int)(base >> 7)), "r"(smem_addr(sOwn))
+                     : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // smem may be released after this
+    }
     if (warp == 0)
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"((uint32_t)SUBN) : "memory");
 }
