@@ -211,7 +211,10 @@ tc_update_mma_kernel(const __grid_constant__ CUtensorMap lat_map, const __grid_c
     __shared__ __align__(8) uint64_t tma_bar;
     __shared__ __align__(8) uint64_t mma_bar;
     __shared__ uint32_t tmem_base_slot;
-    __shared__ uint32_t lut[8];   // thresholds by (v+4)/2; read as lut[(v+4)/2] = byte offset 2*v + 8
+    // thresholds by (neighbour sum nn, own spin s), addressed without arithmetic on s: the word at
+    // byte 16 + 4*nn + off holds thr(v = nn*s) with off = 0 for s = +1 and off = 4 (spin bytes 0, 2
+    // of a word) or 1024 (bytes 1, 3) for s = -1 -- "off" is one masked bit of the spin word itself
+    __shared__ __align__(16) uint32_t lut[512];
 
     const int sb = blockIdx.x + p.slab * 2 * p.nbx * p.nby_loc;   // global sub-block index (RNG map)
     const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
@@ -256,7 +259,12 @@ tc_update_mma_kernel(const __grid_constant__ CUtensorMap lat_map, const __grid_c
                          : "memory");
         }
     }
-    if (t < 5) lut[t] = p.always[t] ? 0xffffffffu : p.thr[t];
+    if (t < 5) {          // t = (nn + 4) / 2
+        const uint32_t plus = p.always[t] ? 0xffffffffu : p.thr[t], minus = p.always[4 - t] ? 0xffffffffu : p.thr[4 - t];
+        lut[2 * t] = plus;
+        lut[2 * t + 1] = minus;
+        lut[256 + 2 * t] = minus;
+    }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -294,7 +302,10 @@ tc_update_mma_kernel(const __grid_constant__ CUtensorMap lat_map, const __grid_c
     const bool has_edge_v = (b == 0) ? (j == 0) : (j == SUBN - 1);
     const int n = j >> 6;                        // which of the reference thread's two runs this row is
     const uint32_t tid0 = (uint32_t)sb * TPS + (uint32_t)(16 * (j & 63));
-    const uint32_t lut_base = smem_addr(lut) + 8;
+    const char* lut_c = reinterpret_cast<const char*>(lut) + 16;
+    // Philox tables of this thread's two calls (n is warp-uniform: rows 0..63 use calls 0,1, rows 64..127 calls 2,3)
+    const uint32_t ta0 = n ? p.st.a[2] : p.st.a[0], tb0 = n ? p.st.b[2] : p.st.b[0], td0 = n ? p.st.d[2] : p.st.d[0];
+    const uint32_t ta1 = n ? p.st.a[3] : p.st.a[1], tb1 = n ? p.st.b[3] : p.st.b[1], td1 = n ? p.st.d[3] : p.st.d[1];
 
     if (t != 0) mbar_wait_parity0(&tma_bar);   // own tile and edge row have landed (thread 0 waited above)
     uint4 own[4];
@@ -344,23 +355,22 @@ tc_update_mma_kernel(const __grid_constant__ CUtensorMap lat_map, const __grid_c
             } else if (FAST) {
                 // one reference thread id per run: fold its constants, then 2 calls of 4 outputs
                 const ThreadConsts tc = make_thread_consts(tid0 + (uint32_t)c, p.st.x1, p.st.k1r3);
+                uint32_t o[2][4];
+                philox_fast(tc, ta0, tb0, td0, p.st.k0, p.st.k1, o[0]);
+                philox_fast(tc, ta1, tb1, td1, p.st.k0, p.st.k1, o[1]);
 #pragma unroll
                 for (int h = 0; h < 2; h++) {
-                    uint32_t o[4];
-                    const int cl = 2 * n + h;   // n is warp-uniform (rows 0..63 / 64..127)
-                    if (n == 0) philox_fast(tc, p.st.a[h], p.st.b[h], p.st.d[h], p.st.k0, p.st.k1, o);
-                    else        philox_fast(tc, p.st.a[2 + h], p.st.b[2 + h], p.st.d[2 + h], p.st.k0, p.st.k1, o);
-                    (void)cl;
-                    uint32_t flipmask = 0;
+                    const uint32_t w0 = w[h], w16 = w[h] >> 16;
 #pragma unroll
                     for (int m = 0; m < 4; m++) {
-                        const int s = (int)(int8_t)(w[h] >> (8 * m));          // +-1
-                        const int v2 = (int)r[8 * cc + 4 * h + m] * (2 * s);   // 2*nn*s = byte offset into lut
-                        uint32_t thr;
-                        asm("ld.shared.u32 %0, [%1];" : "=r"(thr) : "r"(lut_base + (uint32_t)v2));
-                        if (o[m] <= thr) flipmask |= 0xFEu << (8 * m);          // +1 (0x01) <-> -1 (0xFF)
+                        // byte offset 16 + 4*nn + (s == -1 ? 4 or 1024 : 0)
+                        const uint32_t sel = ((m & 2) ? w16 : w0) & ((m & 1) ? 0x400u : 0x4u);
+                        const int off = (int)r[8 * cc + 4 * h + m] * 4 + (int)sel;
+                        const uint32_t thr = *reinterpret_cast<const uint32_t*>(lut_c + off);
+                        asm("{\n.reg .pred q;\nsetp.le.u32 q, %1, %2;\n@q xor.b32 %0, %0, %3;\n}"
+                            : "+r"(w[h])
+                            : "r"(o[h][m]), "r"(thr), "r"(0xFEu << (8 * m)));   // +1 (0x01) <-> -1 (0xFF)
                     }
-                    w[h] ^= flipmask;
                 }
             } else {
 #pragma unroll
