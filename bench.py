@@ -186,37 +186,73 @@ def run_b200(a):
     e2e = None
     if not a.no_e2e:
         pitch = X_COLS // 64
-        hb = torch.empty((rows, pitch), dtype=torch.int32).pin_memory()
-        hw = torch.empty((rows, pitch), dtype=torch.int32).pin_memory()
-        nb, nw = hb.numpy().view(np.uint32), hw.numpy().view(np.uint32)
+        plane_bytes = rows * pitch * 4
+        ksteps = max(1, min(a.steps, a.e2e_steps)) if a.e2e_steps else a.steps
+
+        def pinned():
+            t = torch.empty((rows, pitch), dtype=torch.int32).pin_memory()
+            return t, t.numpy().view(np.uint32)
         b0, w0 = eng.eng.export_bits()
-        nb[:], nw[:] = b0, w0
-        del b0, w0
-        ksteps = max(1, min(a.steps, a.e2e_steps))
+        if world == 1:
+            # replica batch: every step is one job of the batch = upload both planes of a lattice from
+            # pinned memory, S sweeps, spin counts, download both planes; jobs alternate between two
+            # contexts so the copies of one step overlap the kernels of the next (ising_run_batch_from_host)
+            from ising_gpu_b200.engine import IsingEngine
+            eng2 = IsingEngine(X_COLS, rows, seed=a.seed, temp=TEMP, first_device=local)
+            keep, ins, outs = [], [], []
+            for j in range(2):
+                (tb, nb), (tw, nw) = pinned(), pinned()
+                nb[:], nw[:] = b0, w0
+                (tob, nob), (tow, now) = pinned(), pinned()
+                keep += [tb, tw, tob, tow]
+                ins.append((nb, nw)); outs.append((nob, now))
+            del b0, w0
 
-        def e2e_step():
-            eng.eng.import_bits(nb, nw)          # H2D of both colour planes (pinned)
-            eng.refresh_ghosts()                  # ghost rows belong to the uploaded state
-            eng.sweeps(S)
-            eng.eng._ck(eng.eng._L.ising_export_bits(eng.eng._h, 0, nb.ctypes.data, nw.ctypes.data))  # D2H
-            return eng.count_spins()              # D2H of the step's observable
+            def batch(k):
+                return eng.eng.run_batch_from_host(eng2, [ins[j & 1][0] for j in range(k)],
+                                                   [ins[j & 1][1] for j in range(k)], S,
+                                                   [outs[j & 1][0] for j in range(k)],
+                                                   [outs[j & 1][1] for j in range(k)], first_it=eng.it + 1)
+            l0 = eng.eng.launches + eng2.launches
+            batch(2)
+            barrier()
+            t0 = time.perf_counter()
+            counts = batch(ksteps)
+            barrier()
+            dt = time.perf_counter() - t0
+            assert len(set(counts)) == 1 and counts[0][0] + counts[0][1] == X_COLS * rows, counts
+            assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1])
+            e2e_launches = eng.eng.launches + eng2.launches - l0
+            eng2.close()
+            api = ("ising_run_batch_from_host (C ABI, pinned host buffers): per step H2D of both planes, %d sweeps, "
+                   "count kernels, D2H of planes and counts; two contexts, copies overlap the other step's kernels" % S)
+        else:
+            (hb, nb), (hw, nw) = pinned(), pinned()
+            nb[:], nw[:] = b0, w0
+            del b0, w0
 
-        e2e_step()
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(ksteps):
+            def e2e_step():
+                eng.eng.import_bits(nb, nw)          # H2D of both colour planes (pinned)
+                eng.refresh_ghosts()                  # ghost rows belong to the uploaded state
+                eng.sweeps(S)
+                eng.eng._ck(eng.eng._L.ising_export_bits(eng.eng._h, 0, nb.ctypes.data, nw.ctypes.data))  # D2H
+                return eng.count_spins()              # D2H of the step's observable
+
             e2e_step()
-        barrier()
-        dt = time.perf_counter() - t0
-        if world > 1:
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(ksteps):
+                e2e_step()
+            barrier()
+            dt = time.perf_counter() - t0
             t = torch.tensor([dt], device="cuda", dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             dt = float(t.item())
-        plane_bytes = rows * pitch * 4
+            api = ("ising_import_bits + ising_sweeps (fused halo) + ising_export_bits + ising_count_spins per step "
+                   "(C ABI, pinned host buffers), not pipelined")
         e2e = {"value": round(float(X_COLS) * rows * S * ksteps * world / (dt * 1e9), 2), "unit": "flips/ns",
-               "h2d_bytes_per_step": 2 * plane_bytes * world, "d2h_bytes_per_step": (2 * plane_bytes + 16) * world,
-               "steps": ksteps, "api": "ising_import_bits + ising_update_color_part* + ising_export_bits + "
-                                       "ising_count_spins (C ABI, pinned host buffers)"}
+               "h2d_bytes_per_step": 2 * plane_bytes * world, "d2h_bytes_per_step": (2 * plane_bytes + 8) * world,
+               "steps": ksteps, "timer": "host monotonic clock around the synchronised region", "api": api}
 
     out = None
     if rank == 0:
@@ -348,7 +384,7 @@ def main():
     ap.add_argument("--sweeps-per-step", type=int, default=16)
     ap.add_argument("--rows-per-gpu", type=int, default=0)
     ap.add_argument("--seed", type=int, default=463463564571)
-    ap.add_argument("--e2e-steps", type=int, default=4)
+    ap.add_argument("--e2e-steps", type=int, default=0, help="steps of the e2e leg (0 = --steps)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-overlap", action="store_true")

@@ -150,6 +150,17 @@ int ising_run_from_host(ising_ctx* ctx, const uint32_t* black_in, const uint32_t
                         int first_it, int n, uint32_t* black_out, uint32_t* white_out,
                         uint64_t* up, uint64_t* down);
 
+/* Replica batch (ensembles / parameter scans: many independent lattices of the same shape, the
+ * way the reference is used from scripts, optimized/README.md:94-148): lattice k is uploaded from
+ * black_in[k]/white_in[k] (device bit packing, pinned host memory for full overlap), evolved by n
+ * sweeps starting at first_it, counted into up[k]/down[k] and downloaded into black_out[k]/
+ * white_out[k] (entries or the arrays themselves may be NULL).  Jobs alternate between the two
+ * contexts (same shape, same device; ctx_b may be NULL = no overlap), each on its own stream, so
+ * the copies of one job overlap the kernels of the other.  Blocks until the batch is done. */
+int ising_run_batch_from_host(ising_ctx* ctx_a, ising_ctx* ctx_b, int nrep, const uint32_t* const* black_in,
+                              const uint32_t* const* white_in, int first_it, int n, uint32_t* const* black_out,
+                              uint32_t* const* white_out, uint64_t* up, uint64_t* down);
+
 /* ---- multi-process slabs (one process per GPU) ------------------------------------------
  * Device pointer and byte length of one row of a colour plane.  row = -1 is the ghost row
  * above the slab, row = Y the ghost row below it, 0..Y-1 the slab's own rows.  The caller

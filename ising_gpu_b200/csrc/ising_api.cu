@@ -834,6 +834,71 @@ int ising_run_from_host(ising_ctx* c, const uint32_t* black_in, const uint32_t* 
     return ISING_OK;
 }
 
+// Replica batch: job k runs on ctx[k & 1]'s own stream as H2D -> n sweeps -> count -> D2H, everything
+// asynchronous.  The kernels of job k+1 wait (event) for the kernels of job k, so the jobs compute
+// one after the other at full speed while the upload of job k+1 and the download of job k-1 ride
+// on the copy engines -- without that the two streams run in lock-step and the SMs idle during
+// the copies.  A context is reused by job k+2 in stream order.
+int ising_run_batch_from_host(ising_ctx* ctx_a, ising_ctx* ctx_b, int nrep, const uint32_t* const* black_in,
+                              const uint32_t* const* white_in, int first_it, int n, uint32_t* const* black_out,
+                              uint32_t* const* white_out, uint64_t* up, uint64_t* down)
+{
+    ising_ctx* cs[2] = {ctx_a, ctx_b ? ctx_b : ctx_a};
+    if (!ctx_a || nrep < 0 || n < 0 || !black_in || !white_in) return fail(ISING_EINVAL, "bad argument");
+    for (ising_ctx* c : cs) {
+        if (c->dev.size() != 1 || c->ghost_rows) return fail(ISING_ESTATE, "ising_run_batch_from_host needs 1-device, 1-slab contexts");
+        if (c->cfg.X != ctx_a->cfg.X || c->cfg.Y != ctx_a->cfg.Y || c->dev[0].device != ctx_a->dev[0].device)
+            return fail(ISING_EINVAL, "the two contexts must have the same shape and device");
+    }
+    const size_t bytes = (size_t)ctx_a->cfg.Y * ctx_a->pitch * 4;
+    const uint64_t spins = (uint64_t)ctx_a->cfg.Y * (uint64_t)ctx_a->cfg.X;
+    CU_TRY(cudaSetDevice(ctx_a->dev[0].device));
+    unsigned long long* h_counts = nullptr;      // pinned landing zone of the per-job up-counts
+    unsigned long long* d_counts = nullptr;
+    if (up && down && nrep > 0) {
+        CU_TRY(cudaHostAlloc((void**)&h_counts, sizeof(unsigned long long) * nrep, cudaHostAllocDefault));
+        cudaError_t e = cudaMalloc((void**)&d_counts, sizeof(unsigned long long) * nrep);
+        if (e == cudaSuccess) e = cudaMemsetAsync(d_counts, 0, sizeof(unsigned long long) * nrep, cs[0]->dev[0].stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(cs[0]->dev[0].stream);
+        if (e != cudaSuccess) { cudaFreeHost(h_counts); cudaFree(d_counts); return fail(ISING_ECUDA, "batch counters: %s", cudaGetErrorString(e)); }
+    }
+    int rc = ISING_OK;
+    cudaError_t e = cudaSuccess;
+    for (int k = 0; k < nrep && rc == ISING_OK && e == cudaSuccess; k++) {
+        ising_ctx* c = cs[k & 1];
+        DevState& d = c->dev[0];
+        e = cudaMemcpyAsync(local_row(c, d, 0, 0), black_in[k], bytes, cudaMemcpyHostToDevice, d.stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(local_row(c, d, 1, 0), white_in[k], bytes, cudaMemcpyHostToDevice, d.stream);
+        // compute of job k starts when compute of job k-1 (other context) is done
+        if (e == cudaSuccess && k > 0 && cs[0] != cs[1]) e = cudaStreamWaitEvent(d.stream, cs[(k - 1) & 1]->dev[0].ev_color, 0);
+        if (e != cudaSuccess) break;
+        rc = ising_sweeps(c, first_it, n);
+        if (rc != ISING_OK) break;
+        if (d_counts) {
+            for (int col = 0; col < 2; col++) {
+                launch_count(local_row(c, d, col, 0), c->cfg.Y, c->pitch, d_counts + k, d.stream);
+                c->launches++;
+            }
+            e = cudaGetLastError();
+        }
+        if (e == cudaSuccess) e = cudaEventRecord(d.ev_color, d.stream);
+        if (e == cudaSuccess && d_counts) e = cudaMemcpyAsync(h_counts + k, d_counts + k, sizeof(unsigned long long), cudaMemcpyDeviceToHost, d.stream);
+        if (e == cudaSuccess && black_out && black_out[k]) e = cudaMemcpyAsync(black_out[k], local_row(c, d, 0, 0), bytes, cudaMemcpyDeviceToHost, d.stream);
+        if (e == cudaSuccess && white_out && white_out[k]) e = cudaMemcpyAsync(white_out[k], local_row(c, d, 1, 0), bytes, cudaMemcpyDeviceToHost, d.stream);
+    }
+    for (ising_ctx* c : cs) {   // always drain both streams before the staging buffers go away
+        cudaError_t es = cudaStreamSynchronize(c->dev[0].stream);
+        if (e == cudaSuccess) e = es;
+    }
+    if (h_counts && rc == ISING_OK && e == cudaSuccess)
+        for (int k = 0; k < nrep; k++) { up[k] = h_counts[k]; down[k] = spins - h_counts[k]; }
+    if (h_counts) cudaFreeHost(h_counts);
+    if (d_counts) cudaFree(d_counts);
+    if (rc != ISING_OK) return rc;
+    if (e != cudaSuccess) return fail(ISING_ECUDA, "ising_run_batch_from_host: %s", cudaGetErrorString(e));
+    return ISING_OK;
+}
+
 int ising_row_ptr(ising_ctx* c, int dev, int color, int row, void** dptr, size_t* nbytes)
 {
     if (int rc = check_dev(c, dev)) return rc;

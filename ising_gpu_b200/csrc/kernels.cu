@@ -92,6 +92,36 @@ __device__ __forceinline__ void fadd_bit_if_gt(float& acc, uint32_t x, uint32_t 
         : "r"(x), "r"(thr), "f"((float)(1u << bit)));
 }
 
+// Which multiplies of call q (0..7 inside a word) take the FP64 route of philox_map.h: bit q of
+// ISING_DFMA_MASK0 for the M0 multiply, of ISING_DFMA_MASK1 for the M1 multiply.
+#ifndef ISING_DFMA_MASK0
+#define ISING_DFMA_MASK0 0x00
+#endif
+#ifndef ISING_DFMA_MASK1
+#define ISING_DFMA_MASK1 0x00
+#endif
+__device__ __forceinline__ void philox_call(int q, const ThreadConsts& tc, uint32_t ta, uint32_t tb, uint32_t td,
+                                            const uint32_t (&k0)[7], const uint32_t (&k1)[7], uint32_t out[4])
+{
+    const bool f0 = (ISING_DFMA_MASK0 >> q) & 1, f1 = (ISING_DFMA_MASK1 >> q) & 1;   // literals after unrolling
+    if (f0 && f1)  philox_fast_mix<false, false>(tc, ta, tb, td, k0, k1, out);
+    else if (f0)   philox_fast_mix<false, true>(tc, ta, tb, td, k0, k1, out);
+    else if (f1)   philox_fast_mix<true, false>(tc, ta, tb, td, k0, k1, out);
+    else           philox_fast(tc, ta, tb, td, k0, k1, out);
+}
+
+// acc |= (x > thr) << BIT with the compare on the FP64 pipe: xd = 2^52 + x, thrd = 2^52 + thr.
+__device__ __forceinline__ void or_bit_if_gt_f64(uint32_t& acc, double xd, double thrd, int bit)
+{
+    asm("{\n"
+        ".reg .pred p;\n"
+        "setp.gt.f64 p, %1, %2;\n"
+        "@p or.b32 %0, %0, %3;\n"
+        "}\n"
+        : "+r"(acc)
+        : "d"(xd), "d"(thrd), "r"(1u << bit));
+}
+
 // Reject masks of one 32-site word: 8 Philox calls, outputs x,y,z,w -> bits 2q, 16+2q, 2q+1,
 // 17+2q.
 #ifndef ISING_ACC_VARIANT
@@ -113,7 +143,7 @@ __device__ __forceinline__ void word_reject_masks(const ThreadConsts& tc, const 
     for (int q = 7; q >= 0; q--) {
         const int cl = 8 * J + q;
         uint32_t o[4];
-        philox_fast(tc, st.a[cl], st.b[cl], st.d[cl], st.k0, st.k1, o);
+        philox_call(q, tc, st.a[cl], st.b[cl], st.d[cl], st.k0, st.k1, o);
         shift_in_reject(a_lo, o[2], nA);
         shift_in_reject(a_lo, o[0], nA);
         shift_in_reject(a_hi, o[3], nA);
@@ -134,7 +164,7 @@ __device__ __forceinline__ void word_reject_masks(const ThreadConsts& tc, const 
     for (int q = 0; q < 8; q++) {
         const int cl = 8 * J + q;
         uint32_t o[4];
-        philox_fast(tc, st.a[cl], st.b[cl], st.d[cl], st.k0, st.k1, o);
+        philox_call(q, tc, st.a[cl], st.b[cl], st.d[cl], st.k0, st.k1, o);
         or_bit_if_gt(a, o[0], thrA, 2 * q);
         or_bit_if_gt(a, o[1], thrA, 16 + 2 * q);
         or_bit_if_gt(a, o[2], thrA, 2 * q + 1);
@@ -148,6 +178,30 @@ __device__ __forceinline__ void word_reject_masks(const ThreadConsts& tc, const 
     }
     rejA = a;
     rejB = b;
+#elif ISING_ACC_VARIANT == 4
+    // as variant 1, but the two outputs that end a round as the low word of an FP64-pipe result
+    // (x and z) are compared on the FP64 pipe (DSETP), the other two on the ALU (ISETP)
+    uint32_t a = 0, b = 0;
+    const double tAd = __hiloint2double((int)DBL_2P52_HI, (int)thrA), tBd = __hiloint2double((int)DBL_2P52_HI, (int)thrB);
+#pragma unroll
+    for (int q = 0; q < 8; q++) {
+        const int cl = 8 * J + q;
+        uint32_t o[4];
+        double d0, d2;
+        philox_fast_mix<false, false>(tc, st.a[cl], st.b[cl], st.d[cl], st.k0, st.k1, o, &d0, &d2);
+        or_bit_if_gt_f64(a, d0, tAd, 2 * q);
+        or_bit_if_gt(a, o[1], thrA, 16 + 2 * q);
+        or_bit_if_gt_f64(a, d2, tAd, 2 * q + 1);
+        or_bit_if_gt(a, o[3], thrA, 17 + 2 * q);
+        if (NTHR > 1) {
+            or_bit_if_gt_f64(b, d0, tBd, 2 * q);
+            or_bit_if_gt(b, o[1], thrB, 16 + 2 * q);
+            or_bit_if_gt_f64(b, d2, tBd, 2 * q + 1);
+            or_bit_if_gt(b, o[3], thrB, 17 + 2 * q);
+        }
+    }
+    rejA = a;
+    rejB = b;
 #elif ISING_ACC_VARIANT == 2
     // FP32 accumulators (predicated FADD of 2^k): measured no faster -- FMA-lite shares its
     // dispatch with FMA-heavy, so the FADDs still compete with the IMAD.WIDEs.
@@ -156,7 +210,7 @@ __device__ __forceinline__ void word_reject_masks(const ThreadConsts& tc, const 
     for (int q = 0; q < 8; q++) {
         const int cl = 8 * J + q;
         uint32_t o[4];
-        philox_fast(tc, st.a[cl], st.b[cl], st.d[cl], st.k0, st.k1, o);
+        philox_call(q, tc, st.a[cl], st.b[cl], st.d[cl], st.k0, st.k1, o);
         fadd_bit_if_gt(a_lo, o[0], thrA, 2 * q);
         fadd_bit_if_gt(a_hi, o[1], thrA, 2 * q);
         fadd_bit_if_gt(a_lo, o[2], thrA, 2 * q + 1);
@@ -184,7 +238,7 @@ __device__ __forceinline__ void word_reject_masks(const ThreadConsts& tc, const 
     for (int q = 7; q >= 0; q--) {
         const int cl = 8 * J + q;
         uint32_t o[4];
-        philox_fast(tc, st.a[cl], st.b[cl], st.d[cl], st.k0, st.k1, o);
+        philox_call(q, tc, st.a[cl], st.b[cl], st.d[cl], st.k0, st.k1, o);
         if (q >= 8 - NC) {
             shift_in_reject(ca_lo, o[2], nA);
             shift_in_reject(ca_lo, o[0], nA);
@@ -254,6 +308,9 @@ __device__ __forceinline__ uint32_t flip_mask(uint32_t me, uint32_t up, uint32_t
 #ifndef ISING_MIN_BLOCKS
 #define ISING_MIN_BLOCKS 4
 #endif
+#ifndef ISING_PROLOGUE
+#define ISING_PROLOGUE 2
+#endif
 template <bool FAST, bool BONDS, bool PUSH>
 __global__ void __launch_bounds__(UPDATE_THREADS, ISING_MIN_BLOCKS)
 update_color_kernel(const __grid_constant__ CUtensorMap src_tile, const __grid_constant__ CUtensorMap src_row,
@@ -280,8 +337,10 @@ update_color_kernel(const __grid_constant__ CUtensorMap src_tile, const __grid_c
     // own spins: two 32-site words per thread, in flight while the random numbers are made
     uint32_t* const my = dst + (size_t)(y0 + ty) * p.pitch + x0 + tx;
     uint32_t me[2];
+#if ISING_PROLOGUE == 0
     me[0] = my[0];
     me[1] = my[16];
+#endif
     // +-J bonds of the thread's sites (main.cu:575-618): one bit plane per direction
     uint32_t jb[2][4];
     if (BONDS) {
@@ -293,11 +352,31 @@ update_color_kernel(const __grid_constant__ CUtensorMap src_tile, const __grid_c
         }
     }
 
+#if ISING_PROLOGUE == 2
+    // No CTA-wide barrier: warp 0 initialises the mbarrier and then *arrives* on one named barrier
+    // per other warp (ids 1..7, 64 threads each); warp w *syncs* on barrier w only just before it
+    // first touches the mbarrier, ~1000 instructions later, when warp 0 has long since arrived.
+    if (threadIdx.x < 32) {
+        if (threadIdx.x == 0) {
+            mbar_init(&bar, 1);
+            fence_mbar_init();
+        }
+        __threadfence_block();
+        __syncwarp();
+#pragma unroll
+        for (int w = 1; w < UPDATE_THREADS / 32; w++) asm volatile("barrier.cta.arrive %0, 64;" ::"r"(w) : "memory");
+    }
+#else
     if (threadIdx.x == 0) {
         mbar_init(&bar, 1);
         fence_mbar_init();
     }
     __syncthreads();
+#endif
+#if ISING_PROLOGUE != 0
+    me[0] = my[0];     // issued after the mbarrier fence: a fence ahead of them would wait for these loads
+    me[1] = my[16];
+#endif
     if (threadIdx.x == 0) {
         if (PUSH) {   // ghost rows of the source colour must have arrived from the neighbours
             if (y0 == 0) while ((int)(ld_acquire_sys(p.wait_top) - p.wait_value) < 0) { }
@@ -339,6 +418,9 @@ update_color_kernel(const __grid_constant__ CUtensorMap src_tile, const __grid_c
         word_reject_masks<1, 1>(tc, p.st, p.rule.thrA, p.rule.thrB, p.zero, rejA[1], rejB[1]);
     }
 
+#if ISING_PROLOGUE == 2
+    if (threadIdx.x >= 32) asm volatile("barrier.cta.sync %0, 64;" ::"r"((int)(threadIdx.x >> 5)) : "memory");
+#endif
     mbar_wait(&bar, 0);
 
 #pragma unroll

@@ -143,6 +143,60 @@ ISING_HD void philox_fast(const ThreadConsts& tc, uint32_t ta, uint32_t tb, uint
     out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
 
+#if defined(__CUDACC__)
+// ------------------------------------------------------------------------------------------
+// B200 only: the high half of a 32x32 multiply on the FP64 pipe.
+//
+// IMAD.WIDE holds the FMA-heavy pipe of an SM sub-partition for 4 cycles and costs ALU dispatch
+// slots on top; the FP64 pipe of the B200 (16 lanes per sub-partition, one
+// DFMA per 2 cycles) is otherwise idle in this kernel.  For a 32-bit a held as the low word of
+// the double (0x43300000, a) = 2^52 + a,
+//     fma_rz(2^52 + a, M * 2^-32, 2^52 - M * 2^20) = RZ(2^52 + a*M / 2^32) = 2^52 + floor(a*M / 2^32):
+// every operand is exact, the sum lies in [2^52, 2^52 + 2^32) where one ulp is 1, so
+// round-toward-zero is floor() and the low word of the result is mulhi(a, M) -- and its high word
+// is 0x43300000 again, so the XOR of the next Philox round can be done in place on the low word
+// and the pair fed straight into the next DFMA.  The low half of the product is a plain IMAD.
+// ------------------------------------------------------------------------------------------
+constexpr uint32_t DBL_2P52_HI = 0x43300000u;
+
+template <uint32_t M>
+__device__ __forceinline__ double mulhi_dfma(double a_pair)
+{
+    constexpr double MS = (double)M * (1.0 / 4294967296.0);               // M * 2^-32, exact
+    constexpr double C = 4503599627370496.0 - (double)M * 1048576.0;      // 2^52 - M * 2^20, exact
+    return __fma_rz(a_pair, MS, C);
+}
+
+// philox_fast with a choice of multiplier per constant: WIDE0/WIDE1 = true keeps IMAD.WIDE for
+// the M0 / M1 multiply, false sends its high half to the FP64 pipe.
+template <bool WIDE0, bool WIDE1>
+__device__ __forceinline__ void philox_fast_mix(const ThreadConsts& tc, uint32_t ta, uint32_t tb, uint32_t td,
+                                                const uint32_t (&k0)[7], const uint32_t (&k1)[7], uint32_t out[4],
+                                                double* pair0 = nullptr, double* pair2 = nullptr)
+{
+    uint32_t c0 = ta ^ tc.lo1, c2 = tc.hi0p ^ tb, c1 = 0, c3 = 0;
+    double d0 = __hiloint2double((int)DBL_2P52_HI, (int)c0), d2 = __hiloint2double((int)DBL_2P52_HI, (int)c2);
+#pragma unroll
+    for (int r = -1; r < 7; r++) {        // r = -1 is round 3 (c1, c3 and the keys are folded into td, tc.e)
+        uint32_t h0, l0, h1, l1;
+        double h0d = 0.0, h1d = 0.0;
+        if (WIDE0) mulhilo(PHILOX_M0, c0, h0, l0);
+        else { h0d = mulhi_dfma<PHILOX_M0>(d0); l0 = c0 * PHILOX_M0; h0 = (uint32_t)__double2loint(h0d); }
+        if (WIDE1) mulhilo(PHILOX_M1, c2, h1, l1);
+        else { h1d = mulhi_dfma<PHILOX_M1>(d2); l1 = c2 * PHILOX_M1; h1 = (uint32_t)__double2loint(h1d); }
+        if (r < 0) { c0 = h1 ^ td; c2 = h0 ^ tc.e; }
+        else       { c0 = h1 ^ c1 ^ k0[r]; c2 = h0 ^ c3 ^ k1[r]; }
+        c1 = l1; c3 = l0;
+        // the pair that produced h1 / h0 already carries 0x43300000 in its high word
+        if (!WIDE0) d0 = __hiloint2double(WIDE1 ? (int)DBL_2P52_HI : __double2hiint(h1d), (int)c0);
+        if (!WIDE1) d2 = __hiloint2double(WIDE0 ? (int)DBL_2P52_HI : __double2hiint(h0d), (int)c2);
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+    if (pair0) *pair0 = d0;   // (0x43300000, out[0]) and (0x43300000, out[2]): 2^52 + x, ordered like x
+    if (pair2) *pair2 = d2;
+}
+#endif
+
 // Reference thread id of 32-site word c of global row grow (u32 arithmetic, main.cu:514-515).
 ISING_HD uint32_t ref_tid(uint32_t grow, uint32_t c, uint32_t grid_x)
 {

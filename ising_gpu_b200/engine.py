@@ -72,6 +72,8 @@ def load_library():
         "ising_import_bits": ([vp, C.c_int, vp, vp], C.c_int),
         "ising_dump_lattice": ([vp, C.c_char_p], C.c_int),
         "ising_run_from_host": ([vp, vp, vp, C.c_int, C.c_int, vp, vp, u64p, u64p], C.c_int),
+        "ising_run_batch_from_host": ([vp, vp, C.c_int, C.POINTER(vp), C.POINTER(vp), C.c_int, C.c_int,
+                                       C.POINTER(vp), C.POINTER(vp), u64p, u64p], C.c_int),
         "ising_row_ptr": ([vp, C.c_int, C.c_int, C.c_int, C.POINTER(vp), C.POINTER(C.c_size_t)], C.c_int),
         "ising_update_color_part": ([vp, C.c_int, C.c_int, C.c_int, C.c_int, vp], C.c_int),
         "ising_device_count": ([C.POINTER(C.c_int)], C.c_int),
@@ -114,7 +116,7 @@ EXPORTED_SYMBOLS = ("ising_create ising_destroy ising_last_error ising_abi_versi
                     "ising_set_temperature ising_count_spins ising_bond_sum ising_correlation "
                     "ising_export_bonds_ref_layout ising_export_ref_layout "
                     "ising_import_ref_layout ising_export_bits ising_import_bits ising_dump_lattice "
-                    "ising_run_from_host ising_row_ptr ising_update_color_part ising_accept_count "
+                    "ising_run_from_host ising_run_batch_from_host ising_row_ptr ising_update_color_part ising_accept_count "
                     "ising_device_count ising_device_info ising_can_access_peer "
                     "ising_ipc_export ising_ipc_attach ising_push_edges "
                     "ising_accept_table ising_site_random ising_launch_count ising_kernel_name "
@@ -294,6 +296,24 @@ class IsingEngine:
                                              C.byref(up) if counts else None, C.byref(dn) if counts else None))
         self.it += int(n)
         return int(up.value), int(dn.value)
+
+    def run_batch_from_host(self, other, black_in, white_in, n, black_out=None, white_out=None, first_it=1):
+        """Replica batch (ising_run_batch_from_host): lattice k = (black_in[k], white_in[k]) is uploaded,
+        evolved by n sweeps from iteration first_it, counted and downloaded; jobs alternate between this
+        engine and `other` (same shape and device, or None) so copies overlap kernels.  Returns the
+        per-lattice (up, down) counts."""
+        k = len(black_in)
+        assert len(white_in) == k
+
+        def ptrs(arrs):
+            if arrs is None:
+                return None
+            return (C.c_void_p * k)(*[(a.ctypes.data if a is not None else None) for a in arrs])
+        up, dn = (C.c_uint64 * k)(), (C.c_uint64 * k)()
+        self._ck(self._L.ising_run_batch_from_host(self._h, other._h if other is not None else None, k,
+                                                   ptrs(black_in), ptrs(white_in), int(first_it), int(n),
+                                                   ptrs(black_out), ptrs(white_out), up, dn))
+        return [(int(up[i]), int(dn[i])) for i in range(k)]
 
     def ipc_export(self):
         buf = C.create_string_buffer(192)

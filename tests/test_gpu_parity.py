@@ -125,3 +125,30 @@ def test_run_from_host_matches_resident_path(ig):
         bo, wo = np.empty_like(b0), np.empty_like(w0)
         c2 = e2.run_from_host(b0, w0, 4, bo, wo)
         assert np.array_equal(bo, b1) and np.array_equal(wo, w1) and c1 == c2
+
+
+def test_replica_batch_from_host_matches_oracle(ig, oracle):
+    """ising_run_batch_from_host: 5 different lattices (even / odd jobs on different contexts)
+    uploaded from host, 3 sweeps each, downloaded: every replica equals the oracle run from the
+    same start; a NULL second context gives the same result."""
+    X, Y, n = 4096, 64, 3
+    rng = np.random.default_rng(7)
+    starts = [(rng.integers(0, 2**32, size=(Y, X // 64), dtype=np.uint32),
+               rng.integers(0, 2**32, size=(Y, X // 64), dtype=np.uint32)) for _ in range(5)]
+    want = []
+    for b, w in starts:
+        ora = oracle.OracleLattice(X, Y)
+        ora.import_bits(0, b); ora.import_bits(1, w)
+        ora.sweeps(n, TC)
+        want.append((ora.export_bits(0), ora.export_bits(1), ora.count()))
+        ora.close()
+    with ig.IsingEngine(X, Y, temp=TC) as ea, ig.IsingEngine(X, Y, temp=TC) as eb:
+        for other in (eb, None):
+            ob = [np.zeros((Y, X // 64), np.uint32) for _ in starts]
+            ow = [np.zeros((Y, X // 64), np.uint32) for _ in starts]
+            counts = ea.run_batch_from_host(other, [s[0] for s in starts], [s[1] for s in starts], n, ob, ow)
+            for k, (wb, ww, wc) in enumerate(want):
+                assert np.array_equal(ob[k], wb) and np.array_equal(ow[k], ww), "replica %d differs" % k
+                assert counts[k] == wc
+        # outputs and counts are optional
+        assert ea.run_batch_from_host(eb, [starts[0][0]], [starts[0][1]], n) == [want[0][2]]
