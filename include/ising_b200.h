@@ -221,8 +221,9 @@ const char* ising_kernel_name(const ising_ctx* ctx);
  * ========================================================================================== */
 typedef struct ising_tc_ctx ising_tc_ctx;
 
-enum { ISING_TC_NN_MMA = 0,     /* INT8 tensor-core contraction (product path)                 */
-       ISING_TC_NN_STENCIL = 1  /* plain integer 4-neighbour stencil (validation of the MMA)   */ };
+enum { ISING_TC_NN_MMA = 0,      /* INT8 tensor-core contraction, persistent warp-specialised kernel (product path) */
+       ISING_TC_NN_STENCIL = 1,  /* plain integer 4-neighbour stencil (validation of the MMA)                       */
+       ISING_TC_NN_MMA_TILE = 2  /* INT8 tensor-core contraction, one CTA per 128x128 sub-block (A/B, validation)   */ };
 
 /* nbx, nby: lattice columns / rows in units of 256 (-x, -y of ising_tensorcore, main.cu:402-451);
  * alpha: temperature in T_crit units (-a); seed (-s, default 1234). */

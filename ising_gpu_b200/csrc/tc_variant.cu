@@ -15,6 +15,7 @@
 // and the final.txt format.
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <string>
@@ -414,6 +415,385 @@ tc_update_mma_kernel(const __grid_constant__ CUtensorMap lat_map, const __grid_c
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"((uint32_t)SUBN) : "memory");
 }
 
+// ------------------------------------------------------------------------------------------
+// Product kernel, persistent and warp-specialised.  One CTA per SM walks over the sub-blocks
+// blockIdx.x, blockIdx.x + gridDim.x, ... (local tile numbers it = 0, 1, 2, ...).  Warp 16 is the
+// producer (one thread: TMA of the H / V operand tiles and the vertical edge row of tile `it`
+// into stage it % 4 of a shared-memory ring, then the eight tcgen05.mma into TMEM accumulator
+// it % 4 -- all 512 TMEM columns are in use).  Warps 0..15 are two consumer groups of 8 warps;
+// group g owns the tiles it = g, g + 2, ... and therefore the stages / accumulators g and g + 2:
+// TMEM -> registers, edge terms, Philox, Metropolis step.  The tile being updated never touches
+// shared memory: every consumer thread owns 64 consecutive bytes of one row, prefetches them one
+// tile ahead with four 16-byte loads and writes them back with four 16-byte stores.
+// Hand-shake per stage s: full[s] (TMA bytes landed, seen by the producer only) -> mma[s]
+// (tcgen05.commit + a release arrive of the producer) -> free[s] (one arrive per warp of the owning
+// group once its TMEM columns and the edge row are in registers; the producer may then overwrite
+// the accumulator).  The operand tiles of a stage are refilled as soon as its MMAs have completed,
+// so loads run four tiles ahead and a group finds its next tile multiplied when it gets there:
+// the load/MMA latency that the one-tile-per-CTA kernel above exposes on every tile is paid once
+// per CTA, and there is no CTA-wide barrier inside the loop.
+// ------------------------------------------------------------------------------------------
+#ifndef ISING_TC_GROUP_WARPS
+#define ISING_TC_GROUP_WARPS 8
+#endif
+#ifndef ISING_TC_GROUPS
+#define ISING_TC_GROUPS (16 / ISING_TC_GROUP_WARPS)
+#endif
+// consumer warps per tile: 8 = 4 TMEM lane quarters x 2 column halves (64 columns per thread), 4 = one warp per
+// lane quarter (a thread owns a whole row of 128 columns)
+constexpr int PIPE_GROUP_WARPS = ISING_TC_GROUP_WARPS;
+constexpr int PIPE_COLS = SUBN / (PIPE_GROUP_WARPS / 4);   // columns per consumer thread
+constexpr int PIPE_GROUPS = ISING_TC_GROUPS;            // consumer groups; group g takes the CTA's tiles g, g + G, ...
+constexpr int PIPE_CONSUMER_WARPS = PIPE_GROUP_WARPS * PIPE_GROUPS;
+constexpr int PIPE_THREADS = 32 * (PIPE_CONSUMER_WARPS + 1);
+constexpr int PIPE_STAGES = 4;                          // operand stages = TMEM accumulators (4 x 128 = all 512 columns)
+constexpr size_t PIPE_SMEM = (size_t)TILE_BYTES * (1 + 2 * PIPE_STAGES) + 1024;
+static_assert(PIPE_STAGES * SUBN <= 512, "TMEM has 512 columns");
+// registers are allocated per 4 warps: 17 warps count as 20 -> 65536 / (20 * 32) = 102 -> 96 per thread;
+// 25 warps count as 28 -> 73 -> 72 per thread
+constexpr int PIPE_MAXREG = (PIPE_CONSUMER_WARPS <= 16) ? 96 : 72;
+// with 96 registers and 64 columns per thread the tile's own spins are prefetched into registers one tile
+// ahead; otherwise they are prefetched into L2 and loaded at the start of the tile
+constexpr bool PIPE_REG_PREFETCH = (PIPE_MAXREG == 96 && PIPE_COLS == 64);
+constexpr int PIPE_CHUNKS = PIPE_COLS / 16;             // 16-byte chunks = TMEM column groups per thread
+
+__device__ __forceinline__ void mbar_wait_parity(uint64_t* bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "W_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"   // suspend-time hint: sleep in hardware, not in a loop
+        "@p bra D_%=;\n"
+        "bra W_%=;\n"
+        "D_%=:\n"
+        "}\n" ::"r"(smem_addr(bar)),
+        "r"(parity), "r"(0x989680u)
+        : "memory");
+}
+
+struct TileGeom {
+    int sb, a, b, sx, sl;    // global sub-block index, parities, super-block column, super-block row inside the slab
+    long long sup, base;     // byte offset of the super-block / of the sub-block inside this device's slab
+};
+// The tiles tile0, tile0 + step, ... of this colour on this slab, without a division per tile:
+// sub-block index sb = h * 2nbx + bi (update_spins :99-124) is kept as the pair (bi, h).
+struct TileWalk {
+    int bi, h, dbi, dh, two_nbx;
+    __device__ __forceinline__ void init(const TcParams& p, int tile0, int step, int ntiles)
+    {
+        two_nbx = 2 * p.nbx;
+        const int sb = tile0 + p.slab * ntiles;
+        bi = sb % two_nbx; h = sb / two_nbx; dbi = step % two_nbx; dh = step / two_nbx;
+    }
+    __device__ __forceinline__ void advance()
+    {
+        bi += dbi; h += dh;
+        if (bi >= two_nbx) { bi -= two_nbx; h++; }
+    }
+    __device__ __forceinline__ TileGeom geom(const TcParams& p) const
+    {
+        TileGeom g;
+        g.sb = h * two_nbx + bi;
+        g.a = bi & 1;
+        g.b = p.is_black ? g.a : 1 - g.a;          // block_of(): bj = 2h + (black ? a : 1-a)
+        g.sx = bi >> 1;
+        g.sl = h - p.slab * p.nby_loc;             // sy = bj >> 1 = h
+        g.sup = (long long)(g.sl * p.nbx + g.sx) * (SUPN * SUPN);
+        g.base = g.sup + sub_offset(g.a, g.b);
+        return g;
+    }
+};
+
+template <bool FAST>
+__global__ void __maxnreg__(PIPE_MAXREG)
+tc_update_pipe_kernel(const __grid_constant__ CUtensorMap lat_map, const __grid_constant__ CUtensorMap k_map,
+                      int8_t* __restrict__ lat, const __grid_constant__ TcParams p, int ntiles)
+{
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (smem_addr(smem_raw) & 1023u)) & 1023u);
+    uint8_t* sK = smem;                                   // the bidiagonal matrix, loaded once
+    uint8_t* sHV = smem + TILE_BYTES;                     // stage s: H at 2s, V at 2s+1 tiles
+    __shared__ __align__(16) int8_t sEdge[2 * PIPE_STAGES][SUBN];   // edge rows live one round longer than H / V
+    __shared__ __align__(8) uint64_t full_bar[PIPE_STAGES], mma_bar[PIPE_STAGES], free_bar[PIPE_STAGES], k_bar;
+    __shared__ uint32_t tmem_base_slot;
+    __shared__ __align__(16) uint32_t lut[512];           // see tc_update_mma_kernel
+
+    const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+    if (warp == PIPE_CONSUMER_WARPS) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_addr(&tmem_base_slot)),
+                     "r"((uint32_t)(PIPE_STAGES * SUBN))
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (t == 0) {
+        for (int s = 0; s < PIPE_STAGES; s++) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr(&full_bar[s])));
+            // mma[s]: one arrival from tcgen05.commit, one plain (release) arrival of the producer thread after
+            // it has seen full[s] -- the consumers' only wait, which also orders the edge row for them
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 2;" ::"r"(smem_addr(&mma_bar[s])));
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(&free_bar[s])), "r"(PIPE_GROUP_WARPS));
+        }
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr(&k_bar)));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (t < 5) {          // t = (nn + 4) / 2
+        const uint32_t plus = p.always[t] ? 0xffffffffu : p.thr[t], minus = p.always[4 - t] ? 0xffffffffu : p.thr[4 - t];
+        lut[2 * t] = plus;
+        lut[2 * t + 1] = minus;
+        lut[256 + 2 * t] = minus;
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_d = tmem_base_slot;
+    const int first = blockIdx.x, stride = gridDim.x;
+
+    if (warp == PIPE_CONSUMER_WARPS) {
+        // ---------------- producer: one thread drives TMA and the tensor core ----------------
+        if (lane == 0) {
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(&k_bar)),
+                         "r"((uint32_t)TILE_BYTES)
+                         : "memory");
+            // one bidiagonal matrix K+[r][c] = 1 for c = r, r + 1 serves all four cases: taken K-major it is
+            // the "+1" operand, taken MN-major (transposed) the "-1" operand
+            tma_load_rows(sK, &k_map, SUBN, &k_bar);
+            const uint32_t aK = smem_addr(sK);
+            // operand tiles of local tile number `it` (geometry g) into stage it % PIPE_STAGES (its previous MMAs
+            // have completed)
+            const int nslabs = p.nby / p.nby_loc;
+            auto load_tile = [&](int it, const TileGeom& g) {
+                const int s = it & (PIPE_STAGES - 1);
+                uint8_t* sH = sHV + (2 * s) * TILE_BYTES;
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(&full_bar[s])),
+                             "r"((uint32_t)(2 * TILE_BYTES + SUBN))
+                             : "memory");
+                // source sub-blocks: H = (1-a, b) holds the left/right neighbours, V = (a, 1-b) the up/down ones
+                tma_load_rows(sH, &lat_map, (int)((g.sup + sub_offset(1 - g.a, g.b)) >> 7), &full_bar[s]);
+                tma_load_rows(sH + TILE_BYTES, &lat_map, (int)((g.sup + sub_offset(g.a, 1 - g.b)) >> 7), &full_bar[s]);
+                // vertical edge term (add_boundaries): last/first row of sub-block (a, 1-b) of the super-block
+                // above (b == 0) or below (b == 1), which may live in the neighbouring device's slab
+                int d2 = p.slab, sl2;
+                if (g.b == 0) {
+                    sl2 = g.sl - 1;
+                    if (sl2 < 0) { sl2 = p.nby_loc - 1; d2 = (p.slab == 0) ? nslabs - 1 : p.slab - 1; }
+                } else {
+                    sl2 = g.sl + 1;
+                    if (sl2 == p.nby_loc) { sl2 = 0; d2 = (p.slab == nslabs - 1) ? 0 : p.slab + 1; }
+                }
+                const int8_t* edge_row = p.slab_base[d2] + (long long)(sl2 * p.nbx + g.sx) * (SUPN * SUPN) +
+                                         sub_offset(g.a, 1 - g.b) + ((g.b == 0) ? (SUBN - 1) * SUBN : 0);
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                                 smem_addr(sEdge[it & (2 * PIPE_STAGES - 1)])),
+                             "l"(edge_row), "r"((uint32_t)SUBN), "r"(smem_addr(&full_bar[s]))
+                             : "memory");
+            };
+            TileWalk lw;                       // walks PIPE_STAGES tiles ahead of the MMA loop
+            lw.init(p, first, stride, ntiles);
+            for (int k = 0; k < PIPE_STAGES; k++)
+                if (first + k * stride < ntiles) { load_tile(k, lw.geom(p)); lw.advance(); }
+            mbar_wait_parity(&k_bar, 0);
+            int it = 0;
+            for (int tile = first; tile < ntiles; tile += stride, ++it) {
+                const int s = it & (PIPE_STAGES - 1);
+                const uint32_t ph = (uint32_t)(it / PIPE_STAGES) & 1u;
+                const int a = tile & 1, b = p.is_black ? a : 1 - a;   // parities of the sub-block (2nbx and ntiles are even)
+                mbar_wait_parity(&full_bar[s], ph);                               // operands landed
+                if (it >= PIPE_STAGES) mbar_wait_parity(&free_bar[s], ph ^ 1u);   // accumulator s drained by the consumers
+                asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr(&mma_bar[s])) : "memory");
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t aH = smem_addr(sHV + (2 * s) * TILE_BYTES), aV = aH + TILE_BYTES, acc = tmem_d + (uint32_t)(s * SUBN);
+                // k-step of a K-major operand = 32 bytes inside the 128-byte rows, of an MN-major one = 32 rows
+                const uint32_t kh_step = (a == 0) ? 4096u : 32u, kv_step = (b == 0) ? 4096u : 32u;
+                const uint32_t idesc_h = IDESC_I8(0, a == 0), idesc_v = IDESC_I8(b == 0, 1);
+#pragma unroll
+                for (int k = 0; k < 4; k++)      // H (K-major A) x Kh (B): nn[j][i] = H[j][i] + H[j][i+di]
+                    umma_i8(acc, umma_desc_sw128(aH + 32 * k), umma_desc_sw128(aK + kh_step * k), idesc_h, k > 0);
+#pragma unroll
+                for (int k = 0; k < 4; k++)      // Kv (A) x V (MN-major B, in place): += V[j][i] + V[j+dj][i]
+                    umma_i8(acc, umma_desc_sw128(aK + kv_step * k), umma_desc_sw128(aV + 4096 * k), idesc_v, 1u);
+                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                                 smem_addr(&mma_bar[s]))
+                             : "memory");
+                // refill the stage as soon as the tensor core has read it: loads run two tiles ahead
+                if (tile + PIPE_STAGES * stride < ntiles) {
+                    mbar_wait_parity(&mma_bar[s], ph);
+                    load_tile(it + PIPE_STAGES, lw.geom(p));
+                    lw.advance();
+                }
+            }
+        }
+        __syncwarp();
+    } else {
+        // ---------------- consumers: row j = TMEM lane, 64 columns per thread --------------------
+        const int grp = warp / PIPE_GROUP_WARPS;     // consumer group: local tiles grp, grp + PIPE_GROUPS, ...
+        const int j = 32 * (warp & 3) + lane;        // row = TMEM lane (a warp may only touch lanes 32*(warp%4)..)
+        const int half = (warp % PIPE_GROUP_WARPS) >> 2;   // first column = PIPE_COLS * half (0 when a thread owns the row)
+        const int colbase = PIPE_COLS * half;
+        const int n = j >> 6;                        // which of the reference thread's two runs this row is
+        const char* lut_c = reinterpret_cast<const char*>(lut) + 16;
+        // Philox tables of this thread's two calls (n is warp-uniform: rows 0..63 use calls 0,1, rows 64..127 calls 2,3)
+        const uint32_t ta0 = n ? p.st.a[2] : p.st.a[0], tb0 = n ? p.st.b[2] : p.st.b[0], td0 = n ? p.st.d[2] : p.st.d[0];
+        const uint32_t ta1 = n ? p.st.a[3] : p.st.a[1], tb1 = n ? p.st.b[3] : p.st.b[1], td1 = n ? p.st.d[3] : p.st.d[1];
+
+        // own spins and the horizontal edge spin of the NEXT tile are fetched while the current one is worked on
+        const int first_g = first + grp * stride, stride_g = PIPE_GROUPS * stride;
+        TileWalk cw;
+        cw.init(p, first_g, stride_g, ntiles);
+        TileGeom gn = cw.geom(p);
+        uint4 own_n[PIPE_REG_PREFETCH ? PIPE_CHUNKS : 1];
+        int edge_n = 0;
+        auto own_ptr = [&](const TileGeom& g) { return lat + g.base + (long long)j * SUBN + colbase; };
+        // horizontal edge term: lands on column 0 (a == 0) or 127 (a == 1) of every row; it is column 127 of the
+        // block to the left (a == 0) / column 0 of the block to the right, same slab.  nullptr = not this thread's.
+        auto edge_ptr = [&](const TileGeom& g) -> const int8_t* {
+            const int edge_col = (g.a == 0) ? 0 : SUBN - 1;
+            if (edge_col < colbase || edge_col >= colbase + PIPE_COLS) return nullptr;
+            const int sx2 = (g.a == 0) ? (g.sx == 0 ? p.nbx - 1 : g.sx - 1) : (g.sx == p.nbx - 1 ? 0 : g.sx + 1);
+            return lat + (long long)(g.sl * p.nbx + sx2) * (SUPN * SUPN) + sub_offset(1 - g.a, g.b) + (long long)j * SUBN +
+                   ((g.a == 0) ? SUBN - 1 : 0);
+        };
+        // (volatile asm: the compiler must not sink these loads to their first use)
+        auto fetch = [&](const TileGeom& g, uint4* o, int& e) {
+            const int8_t* src = own_ptr(g);
+#pragma unroll
+            for (int ch = 0; ch < PIPE_CHUNKS; ch++)
+                asm volatile("ld.global.v4.u32 {%0, %1, %2, %3}, [%4];"
+                             : "=r"(o[ch].x), "=r"(o[ch].y), "=r"(o[ch].z), "=r"(o[ch].w)
+                             : "l"(src + 16 * ch));
+            e = 0;
+            if (const int8_t* ep = edge_ptr(g)) asm volatile("ld.global.s8 %0, [%1];" : "=r"(e) : "l"(ep));
+        };
+        auto l2_prefetch = [&](const TileGeom& g) {
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(own_ptr(g)));
+            if (PIPE_COLS > 64) asm volatile("prefetch.global.L2 [%0];" ::"l"(own_ptr(g) + 64));
+            if (const int8_t* ep = edge_ptr(g)) asm volatile("prefetch.global.L2 [%0];" ::"l"(ep));
+        };
+        if (PIPE_REG_PREFETCH && first_g < ntiles) fetch(gn, own_n, edge_n);
+
+        int it = grp;                                // local tile number as the producer counts them
+        for (int tile = first_g; tile < ntiles; tile += stride_g, it += PIPE_GROUPS) {
+            const int s = it & (PIPE_STAGES - 1);
+            const uint32_t ph = (uint32_t)(it / PIPE_STAGES) & 1u;
+            const TileGeom g = gn;
+            uint4 own[PIPE_CHUNKS];
+            int edge_h;
+            if (PIPE_REG_PREFETCH) {
+#pragma unroll
+                for (int ch = 0; ch < PIPE_CHUNKS; ch++) own[ch] = own_n[ch];
+                edge_h = edge_n;
+            } else {
+                fetch(g, own, edge_h);
+            }
+            if (tile + stride_g < ntiles) {
+                cw.advance();
+                gn = cw.geom(p);
+                if (PIPE_REG_PREFETCH) fetch(gn, own_n, edge_n);
+                else                   l2_prefetch(gn);
+            }
+            const int edge_col = (g.a == 0) ? 0 : SUBN - 1;
+            // vertical edge term: a whole row, only for the first (b == 0) or last (b == 1) row of the block
+            const bool has_edge_v = (g.b == 0) ? (j == 0) : (j == SUBN - 1);
+            const uint32_t tid0 = (uint32_t)g.sb * TPS + (uint32_t)(16 * (j & 63));
+            int8_t* const dst = lat + g.base + (long long)j * SUBN + colbase;
+
+            // neighbour sums are in TMEM, the edge row in shared memory.  (full[s] itself must not be waited
+            // on here: the producer refills the stage right after the MMAs and the barrier may already be
+            // two phases ahead of a slow consumer.)
+            mbar_wait_parity(&mma_bar[s], ph);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+
+#pragma unroll
+            for (int gq = 0; gq < PIPE_CHUNKS; gq++) {  // groups of 16 columns
+                uint32_t r[16];
+                const int col0 = colbase + 16 * gq;
+                const uint32_t taddr = tmem_d + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(s * SUBN + col0);
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+                    "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+                    "tcgen05.wait::ld.sync.aligned;"
+                    : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+                      "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                    : "r"(taddr)
+                    : "memory");
+                // terms from across the sub-block edge (add_boundaries)
+                if (col0 == 0 && edge_col == 0) r[0] += (uint32_t)edge_h;
+                if (col0 == SUBN - 16 && edge_col == SUBN - 1) r[15] += (uint32_t)edge_h;
+                if (has_edge_v) {
+#pragma unroll
+                    for (int q4 = 0; q4 < 4; q4++) {
+                        const uint32_t e4 = *reinterpret_cast<const uint32_t*>(sEdge[it & (2 * PIPE_STAGES - 1)] + col0 + 4 * q4);
+#pragma unroll
+                        for (int q = 0; q < 4; q++) r[4 * q4 + q] += (uint32_t)(int)(int8_t)(e4 >> (8 * q));
+                    }
+                }
+                if (gq == PIPE_CHUNKS - 1) {
+                    // this warp is done with accumulator s and with its edge row: hand the accumulator back
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0)
+                        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr(&free_bar[s])) : "memory");
+                }
+                uint4& w4 = own[gq];
+#pragma unroll
+                for (int cc = 0; cc < 2; cc++) {        // 2 runs of 8 spins per group
+                    const int c = (col0 >> 3) + cc;     // run index inside the row, 0..15
+                    uint32_t w[2] = {cc ? w4.z : w4.x, cc ? w4.w : w4.y};   // 8 own spins, one per byte
+                    if (FAST) {
+                        // one reference thread id per run: fold its constants, then 2 calls of 4 outputs
+                        const ThreadConsts tc = make_thread_consts(tid0 + (uint32_t)c, p.st.x1, p.st.k1r3);
+                        uint32_t o[2][4];
+                        philox_fast(tc, ta0, tb0, td0, p.st.k0, p.st.k1, o[0]);
+                        philox_fast(tc, ta1, tb1, td1, p.st.k0, p.st.k1, o[1]);
+#pragma unroll
+                        for (int h = 0; h < 2; h++) {
+                            const uint32_t w0 = w[h], w16 = w[h] >> 16;
+#pragma unroll
+                            for (int m = 0; m < 4; m++) {
+                                // byte offset 16 + 4*nn + (s == -1 ? 4 or 1024 : 0)
+                                const uint32_t sel = ((m & 2) ? w16 : w0) & ((m & 1) ? 0x400u : 0x4u);
+                                const int off = (int)r[8 * cc + 4 * h + m] * 4 + (int)sel;
+                                const uint32_t thr = *reinterpret_cast<const uint32_t*>(lut_c + off);
+                                asm("{\n.reg .pred q;\nsetp.le.u32 q, %1, %2;\n@q xor.b32 %0, %0, %3;\n}"
+                                    : "+r"(w[h])
+                                    : "r"(o[h][m]), "r"(thr), "r"(0xFEu << (8 * m)));   // +1 (0x01) <-> -1 (0xFF)
+                            }
+                        }
+                    } else {
+#pragma unroll
+                        for (int h = 0; h < 2; h++) {
+                            uint32_t o[4];
+                            const uint64_t ctr = p.call0 + 2 * n + h;
+                            philox4x32_10((uint32_t)ctr, (uint32_t)(ctr >> 32), tid0 + (uint32_t)c, 0u, p.key0, p.key1, o);
+#pragma unroll
+                            for (int m = 0; m < 4; m++) {
+                                const int sp = (int)(int8_t)(w[h] >> (8 * m));
+                                const int k = ((int)r[8 * cc + 4 * h + m] * sp + 4) >> 1;
+                                if (p.always[k] || (!p.never[k] && o[m] <= p.thr[k])) w[h] ^= 0xFEu << (8 * m);
+                            }
+                        }
+                    }
+                    if (cc) {
+                        // 16 bytes finished: store them now, long before their registers are reused
+                        asm volatile("st.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 16 * gq), "r"(w4.x), "r"(w4.y),
+                                     "r"(w[0]), "r"(w[1])
+                                     : "memory");
+                    } else {
+                        w4.x = w[0]; w4.y = w[1];
+                    }
+                }
+            }
+        }
+    }
+
+    // ---- release TMEM -------------------------------------------------------------------------
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == PIPE_CONSUMER_WARPS)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"((uint32_t)(PIPE_STAGES * SUBN))
+                     : "memory");
+}
+
 // init_spins: element t <- first output of Philox(subsequence t, offset 0); uniform < 0.5 -> -1
 __global__ void __launch_bounds__(256) tc_init_kernel(int8_t* __restrict__ lat, long long n, long long t0, uint32_t key0,
                                                      uint32_t key1, uint32_t thr_half)
@@ -477,10 +857,12 @@ struct TcDev {
     long long* d_sum = nullptr;
     cudaStream_t stream = nullptr;
     cudaEvent_t e0 = nullptr, e1 = nullptr, ev_color = nullptr;
+    int sms = 148;
 };
 
 struct ising_tc_ctx {
     int nbx = 0, nby = 0, ngpus = 1, nby_loc = 0, nn_path = ISING_TC_NN_MMA;
+    int nn_kernel = 0;   // 0 = persistent pipeline (product), 1 = one CTA per sub-block (ISING_TC_KERNEL=tile)
     long long n = 0, n_loc = 0;
     uint64_t seed = 0;
     float alpha = 0, accept[5];
@@ -507,6 +889,7 @@ static int tc_create_impl(int nbx, int nby, uint64_t seed, float alpha, int firs
     if (first_device < 0 || first_device + ngpus > avail) return tc_fail(ISING_EINVAL, "devices %d..%d requested, %d visible", first_device, first_device + ngpus - 1, avail);
     ising_tc_ctx* c = new ising_tc_ctx();
     c->nbx = nbx; c->nby = nby; c->ngpus = ngpus; c->nby_loc = nby / ngpus; c->seed = seed; c->alpha = alpha;
+    if (const char* k = getenv("ISING_TC_KERNEL")) c->nn_kernel = (strcmp(k, "tile") == 0) ? 1 : 0;   // developer A/B switch
     c->n = (long long)nbx * nby * SUPN * SUPN;
     c->n_loc = c->n / ngpus;
     c->dev.resize(ngpus);
@@ -544,6 +927,7 @@ static int tc_create_impl(int nbx, int nby, uint64_t seed, float alpha, int firs
             if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return bail(tc_fail(ISING_ECUDA, "peer access: %s", cudaGetErrorString(e)));
             cudaGetLastError();
         }
+        cudaDeviceGetAttribute(&d.sms, cudaDevAttrMultiProcessorCount, d.device);
         if ((e = cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking)) != cudaSuccess ||
             (e = cudaMalloc(&d.lat, (size_t)c->n_loc)) != cudaSuccess || (e = cudaMalloc(&d.d_sum, sizeof(long long))) != cudaSuccess ||
             (e = cudaMalloc(&d.kmat, k.size())) != cudaSuccess ||
@@ -611,15 +995,24 @@ static int tc_launch_color(ising_tc_ctx* c, bool black, uint64_t iter, int8_t** 
         p.call0 = (2ull * iter + (black ? 0 : 1)) * 4ull;   // offset (2*iter [+1])*16 draws, main.cu:269/:294
         const int ctas = 2 * c->nbx * c->nby_loc;
         int8_t* nn = nn_out ? nn_out[i] : nullptr;
-        if (c->nn_path == ISING_TC_NN_MMA) {
+        if (c->nn_path == ISING_TC_NN_MMA || c->nn_path == ISING_TC_NN_MMA_TILE) {
             const size_t smem = 4 * TILE_BYTES + 1024;
             TC_TRY(cudaFuncSetAttribute(tc_update_mma_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             TC_TRY(cudaFuncSetAttribute(tc_update_mma_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             TC_TRY(cudaFuncSetAttribute(tc_update_mma_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             p.st = make_step_tables_at(c->seed, p.call0);
-            if (nn)           tc_update_mma_kernel<true, false><<<ctas, MMA_THREADS, smem, d.stream>>>(d.lat_map, d.k_map, d.lat, nn, p);
-            else if (p.fast)  tc_update_mma_kernel<false, true><<<ctas, MMA_THREADS, smem, d.stream>>>(d.lat_map, d.k_map, d.lat, nullptr, p);
-            else              tc_update_mma_kernel<false, false><<<ctas, MMA_THREADS, smem, d.stream>>>(d.lat_map, d.k_map, d.lat, nullptr, p);
+            if (nn) {
+                tc_update_mma_kernel<true, false><<<ctas, MMA_THREADS, smem, d.stream>>>(d.lat_map, d.k_map, d.lat, nn, p);
+            } else if (c->nn_kernel == 1 || c->nn_path == ISING_TC_NN_MMA_TILE) {   // one CTA per sub-block (A/B, validation)
+                if (p.fast) tc_update_mma_kernel<false, true><<<ctas, MMA_THREADS, smem, d.stream>>>(d.lat_map, d.k_map, d.lat, nullptr, p);
+                else        tc_update_mma_kernel<false, false><<<ctas, MMA_THREADS, smem, d.stream>>>(d.lat_map, d.k_map, d.lat, nullptr, p);
+            } else {                          // product: persistent, warp-specialised pipeline
+                TC_TRY(cudaFuncSetAttribute(tc_update_pipe_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PIPE_SMEM));
+                TC_TRY(cudaFuncSetAttribute(tc_update_pipe_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PIPE_SMEM));
+                const int grid = ctas < d.sms ? ctas : d.sms;   // one persistent CTA per SM
+                if (p.fast) tc_update_pipe_kernel<true><<<grid, PIPE_THREADS, PIPE_SMEM, d.stream>>>(d.lat_map, d.k_map, d.lat, p, ctas);
+                else        tc_update_pipe_kernel<false><<<grid, PIPE_THREADS, PIPE_SMEM, d.stream>>>(d.lat_map, d.k_map, d.lat, p, ctas);
+            }
         } else {
             if (nn) tc_update_stencil_kernel<true><<<ctas, SUBN, 0, d.stream>>>(d.lat, nn, p);
             else    tc_update_stencil_kernel<false><<<ctas, SUBN, 0, d.stream>>>(d.lat, nullptr, p);
@@ -668,7 +1061,8 @@ int ising_tc_destroy(ising_tc_ctx* c)
 
 int ising_tc_set_nn_path(ising_tc_ctx* c, int path)
 {
-    if (!c || (path != ISING_TC_NN_MMA && path != ISING_TC_NN_STENCIL)) TC_RET(tc_fail(ISING_EINVAL, "bad nn path"));
+    if (!c || (path != ISING_TC_NN_MMA && path != ISING_TC_NN_STENCIL && path != ISING_TC_NN_MMA_TILE))
+        TC_RET(tc_fail(ISING_EINVAL, "bad nn path"));
     c->nn_path = path;
     return ISING_OK;
 }

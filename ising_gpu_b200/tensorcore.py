@@ -8,7 +8,7 @@ import numpy as np
 
 from .engine import IsingError, load_library
 
-NN_MMA, NN_STENCIL = 0, 1
+NN_MMA, NN_STENCIL, NN_MMA_TILE = 0, 1, 2   # persistent tcgen05 pipeline (product), integer stencil, one CTA per tile
 
 
 class TensorcoreEngine:

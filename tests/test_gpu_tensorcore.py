@@ -16,7 +16,7 @@ def _pair(oracle, nbx, nby, seed, alpha, nn_path):
     return eng, ora
 
 
-@pytest.mark.parametrize("nn_path", [0, 1])
+@pytest.mark.parametrize("nn_path", [0, 1, 2])
 @pytest.mark.parametrize("nbx,nby,alpha", [(1, 1, 1.0), (2, 1, 0.661030), (1, 3, 1.0), (3, 2, 2.0)])
 def test_variant_matches_oracle(oracle, nbx, nby, alpha, nn_path):
     eng, ora = _pair(oracle, nbx, nby, 1234, alpha, nn_path)
@@ -30,6 +30,32 @@ def test_variant_matches_oracle(oracle, nbx, nby, alpha, nn_path):
     assert eng.sum() == ora.sum()
     assert np.array_equal(eng.true_lattice(), ora.true_lattice())
     eng.close()
+
+
+@pytest.mark.parametrize("alpha", [0.661030, 0.05])
+def test_persistent_pipeline_many_tiles_per_cta(oracle, alpha):
+    """24 x 24 super-blocks = 1152 sub-blocks per colour: every persistent CTA walks ~8 tiles, so the
+    4-stage operand ring, the TMEM accumulators and every mbarrier phase wrap around several times.
+    alpha = 0.05 takes the generic (non-fast) acceptance path."""
+    eng, ora = _pair(oracle, 24, 24, 4321, alpha, 0)
+    eng.init(); ora.init()
+    for it in range(3):
+        eng.update(1); ora.update(1)
+        assert np.array_equal(eng.storage(), ora.storage()), "iteration %d" % (it + 1)
+    assert eng.sum() == ora.sum()
+    eng.close()
+
+
+def test_pipeline_and_tile_kernels_agree_at_scale():
+    """8192^2 (2048 sub-blocks per colour, ~14 per CTA), 10 iterations: identical storage."""
+    from ising_gpu_b200.tensorcore import TensorcoreEngine
+    out = []
+    for path in (0, 2):
+        with TensorcoreEngine(32, 32, seed=1234, alpha=0.661030, nn_path=path) as eng:
+            eng.init(); eng.update(10)
+            out.append((eng.storage().copy(), eng.sum()))
+    assert out[0][1] == out[1][1]
+    assert np.array_equal(out[0][0], out[1][0])
 
 
 def test_device_accept_table_close_to_host_expf(oracle):
@@ -57,8 +83,8 @@ def _ngpus():
     return torch.cuda.device_count()
 
 
-@pytest.mark.parametrize("nn_path", [0, 1])
-@pytest.mark.parametrize("nbx,nby,ngpus", [(2, 2, 2), (1, 4, 2), (3, 4, 4), (1, 8, 8)])
+@pytest.mark.parametrize("nn_path", [0, 1, 2])
+@pytest.mark.parametrize("nbx,nby,ngpus", [(2, 2, 2), (1, 4, 2), (16, 16, 2), (3, 4, 4), (1, 8, 8)])
 def test_variant_multi_gpu_matches_oracle(oracle, nbx, nby, ngpus, nn_path):
     """-g N (tensorcore/main.cu:240-298): super-block rows split over N devices; the global thread
     ids keep the random numbers -- and therefore the lattice -- independent of N."""
