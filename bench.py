@@ -226,6 +226,56 @@ def run_b200(a):
             eng2.close()
             api = ("ising_run_batch_from_host (C ABI, pinned host buffers): per step H2D of both planes, %d sweeps, "
                    "count kernels, D2H of planes and counts; two contexts, copies overlap the other step's kernels" % S)
+        elif a.halo == "fused":
+            # the same replica batch on every rank's slab (ising_run_slab_batch_from_host): per step H2D of the
+            # slab's planes and white ghost rows, S sweeps with the fused halo push between the ranks, counts,
+            # D2H of the planes; two contexts per rank so that copies overlap the other step's kernels
+            with torch.cuda.stream(torch.cuda.Stream()):   # SlabEngine works on the stream current at construction
+                eng2 = SlabEngine(X_COLS, rows, TEMP, a.seed, rank=rank, world=world, device=local, halo="fused")
+            eng2.init_lattice()
+            # one unpipelined step first: gives the ghost rows that belong to the uploaded state and the
+            # result the pipelined steps must reproduce
+            it0 = eng.it
+            eng.eng.import_bits(b0, w0)
+            eng.refresh_ghosts()
+            ghosts = eng.white_ghost_rows()
+            eng.sweeps(S)
+            want_b, want_w = eng.eng.export_bits()
+            want_counts = eng.count_spins()
+            eng.it = eng2.it = it0
+            keep, ins, outs = [], [], []
+            for j in range(2):
+                (tb, nb), (tw, nw) = pinned(), pinned()
+                nb[:], nw[:] = b0, w0
+                (tob, nob), (tow, now) = pinned(), pinned()
+                keep += [tb, tw, tob, tow]
+                ins.append((nb, nw)); outs.append((nob, now))
+            del b0, w0
+            tg = torch.empty((2, pitch), dtype=torch.int32).pin_memory()
+            ng = tg.numpy().view(np.uint32)
+            ng[:] = ghosts
+
+            def batch(k):
+                return eng.run_batch_from_host(eng2, [ins[j & 1][0] for j in range(k)], [ins[j & 1][1] for j in range(k)],
+                                               [ng] * k, S, [outs[j & 1][0] for j in range(k)],
+                                               [outs[j & 1][1] for j in range(k)])
+            batch(2)
+            barrier()
+            t0 = time.perf_counter()
+            counts = batch(ksteps)
+            barrier()
+            dt = time.perf_counter() - t0
+            assert all(c == want_counts for c in counts), (counts, want_counts)
+            for ob, ow in outs[:min(2, ksteps)]:
+                assert np.array_equal(ob, want_b) and np.array_equal(ow, want_w), "pipelined slab batch differs"
+            del want_b, want_w
+            t = torch.tensor([dt], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+            eng2.close()
+            api = ("ising_run_slab_batch_from_host (C ABI, pinned host buffers): per step and rank H2D of the slab's planes "
+                   "and white ghost rows, %d sweeps with the fused halo push, count kernels, D2H of planes and counts; "
+                   "two contexts per rank, copies overlap the other step's kernels" % S)
         else:
             (hb, nb), (hw, nw) = pinned(), pinned()
             nb[:], nw[:] = b0, w0
@@ -251,7 +301,7 @@ def run_b200(a):
             api = ("ising_import_bits + ising_sweeps (fused halo) + ising_export_bits + ising_count_spins per step "
                    "(C ABI, pinned host buffers), not pipelined")
         e2e = {"value": round(float(X_COLS) * rows * S * ksteps * world / (dt * 1e9), 2), "unit": "flips/ns",
-               "h2d_bytes_per_step": 2 * plane_bytes * world, "d2h_bytes_per_step": (2 * plane_bytes + 8) * world,
+               "h2d_bytes_per_step": (2 * plane_bytes + (2 * pitch * 4 if world > 1 and a.halo == "fused" else 0)) * world, "d2h_bytes_per_step": (2 * plane_bytes + 8) * world,
                "steps": ksteps, "timer": "host monotonic clock around the synchronised region", "api": api}
 
     out = None

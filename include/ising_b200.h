@@ -161,6 +161,18 @@ int ising_run_batch_from_host(ising_ctx* ctx_a, ising_ctx* ctx_b, int nrep, cons
                               const uint32_t* const* white_in, int first_it, int n, uint32_t* const* black_out,
                               uint32_t* const* white_out, uint64_t* up, uint64_t* down);
 
+/* The same for one slab of a lattice split over several processes (one per GPU, peers attached with
+ * ising_ipc_attach, fused halo push): every rank calls it with its own slab of replica k and the
+ * white ghost rows that go with it, ghosts_in[k] = 2 rows of X/64 words: the white row just above
+ * the slab and the one just below (the neighbouring slabs' boundary rows of the same replica; the
+ * black ones are not needed, a sweep starts with the black update, which reads white only).  The
+ * halo of the sweeps travels from kernel to kernel as in ising_sweeps; before a context's ghost rows
+ * are overwritten with the next replica's, a device-side wait makes sure the neighbours' last pushes
+ * of the previous one have landed.  up[k]/down[k] count this slab only. */
+int ising_run_slab_batch_from_host(ising_ctx* ctx_a, ising_ctx* ctx_b, int nrep, const uint32_t* const* black_in,
+                                   const uint32_t* const* white_in, const uint32_t* const* ghosts_in, int first_it, int n,
+                                   uint32_t* const* black_out, uint32_t* const* white_out, uint64_t* up, uint64_t* down);
+
 /* ---- multi-process slabs (one process per GPU) ------------------------------------------
  * Device pointer and byte length of one row of a colour plane.  row = -1 is the ghost row
  * above the slab, row = Y the ghost row below it, 0..Y-1 the slab's own rows.  The caller

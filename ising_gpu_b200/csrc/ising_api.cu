@@ -839,14 +839,17 @@ int ising_run_from_host(ising_ctx* c, const uint32_t* black_in, const uint32_t* 
 // one after the other at full speed while the upload of job k+1 and the download of job k-1 ride
 // on the copy engines -- without that the two streams run in lock-step and the SMs idle during
 // the copies.  A context is reused by job k+2 in stream order.
-int ising_run_batch_from_host(ising_ctx* ctx_a, ising_ctx* ctx_b, int nrep, const uint32_t* const* black_in,
-                              const uint32_t* const* white_in, int first_it, int n, uint32_t* const* black_out,
-                              uint32_t* const* white_out, uint64_t* up, uint64_t* down)
+static int run_batch(ising_ctx* ctx_a, ising_ctx* ctx_b, int nrep, const uint32_t* const* black_in,
+                     const uint32_t* const* white_in, const uint32_t* const* ghosts_in, int first_it, int n,
+                     uint32_t* const* black_out, uint32_t* const* white_out, uint64_t* up, uint64_t* down)
 {
     ising_ctx* cs[2] = {ctx_a, ctx_b ? ctx_b : ctx_a};
     if (!ctx_a || nrep < 0 || n < 0 || !black_in || !white_in) return fail(ISING_EINVAL, "bad argument");
     for (ising_ctx* c : cs) {
-        if (c->dev.size() != 1 || c->ghost_rows) return fail(ISING_ESTATE, "ising_run_batch_from_host needs 1-device, 1-slab contexts");
+        if (c->dev.size() != 1) return fail(ISING_ESTATE, "replica batches need 1-device contexts");
+        if (!ghosts_in && c->ghost_rows) return fail(ISING_ESTATE, "ising_run_batch_from_host needs 1-slab contexts");
+        if (ghosts_in && !(c->ghost_rows && c->fused && c->dev[0].up_flags))
+            return fail(ISING_ESTATE, "ising_run_slab_batch_from_host needs slab contexts with attached peers (ising_ipc_attach)");
         if (c->cfg.X != ctx_a->cfg.X || c->cfg.Y != ctx_a->cfg.Y || c->dev[0].device != ctx_a->dev[0].device)
             return fail(ISING_EINVAL, "the two contexts must have the same shape and device");
     }
@@ -867,6 +870,25 @@ int ising_run_batch_from_host(ising_ctx* ctx_a, ising_ctx* ctx_b, int nrep, cons
     for (int k = 0; k < nrep && rc == ISING_OK && e == cudaSuccess; k++) {
         ising_ctx* c = cs[k & 1];
         DevState& d = c->dev[0];
+        if (ghosts_in) {
+            // the neighbours' last pushes of the previous replica on this context must have landed before
+            // the ghost rows are overwritten from the host
+            const unsigned int tiles_x = (unsigned int)(c->pitch / TW);
+            launch_halo_wait(d.d_flags, (unsigned int)(c->pushes_done[0] * tiles_x), (unsigned int)(c->pushes_done[1] * tiles_x),
+                             d.stream);
+            c->launches++;
+            e = cudaGetLastError();
+            // Only the WHITE ghost rows come from the host: the first colour step (black) reads nothing else,
+            // and the black ghost rows are written by the neighbours' first black step -- which may run ahead
+            // of this upload, so a host copy of them could overwrite fresher data.
+            const size_t row_bytes = (size_t)c->pitch * 4;
+            if (e == cudaSuccess)
+                e = cudaMemcpyAsync(local_row(c, d, 1, -1), ghosts_in[k], row_bytes, cudaMemcpyHostToDevice, d.stream);
+            if (e == cudaSuccess)
+                e = cudaMemcpyAsync(local_row(c, d, 1, c->cfg.Y), ghosts_in[k] + c->pitch, row_bytes, cudaMemcpyHostToDevice,
+                                    d.stream);
+            if (e != cudaSuccess) break;
+        }
         e = cudaMemcpyAsync(local_row(c, d, 0, 0), black_in[k], bytes, cudaMemcpyHostToDevice, d.stream);
         if (e == cudaSuccess) e = cudaMemcpyAsync(local_row(c, d, 1, 0), white_in[k], bytes, cudaMemcpyHostToDevice, d.stream);
         // compute of job k starts when compute of job k-1 (other context) is done
@@ -897,6 +919,21 @@ int ising_run_batch_from_host(ising_ctx* ctx_a, ising_ctx* ctx_b, int nrep, cons
     if (rc != ISING_OK) return rc;
     if (e != cudaSuccess) return fail(ISING_ECUDA, "ising_run_batch_from_host: %s", cudaGetErrorString(e));
     return ISING_OK;
+}
+
+int ising_run_batch_from_host(ising_ctx* ctx_a, ising_ctx* ctx_b, int nrep, const uint32_t* const* black_in,
+                              const uint32_t* const* white_in, int first_it, int n, uint32_t* const* black_out,
+                              uint32_t* const* white_out, uint64_t* up, uint64_t* down)
+{
+    return run_batch(ctx_a, ctx_b, nrep, black_in, white_in, nullptr, first_it, n, black_out, white_out, up, down);
+}
+
+int ising_run_slab_batch_from_host(ising_ctx* ctx_a, ising_ctx* ctx_b, int nrep, const uint32_t* const* black_in,
+                                   const uint32_t* const* white_in, const uint32_t* const* ghosts_in, int first_it, int n,
+                                   uint32_t* const* black_out, uint32_t* const* white_out, uint64_t* up, uint64_t* down)
+{
+    if (!ghosts_in) return fail(ISING_EINVAL, "ghosts_in is required");
+    return run_batch(ctx_a, ctx_b, nrep, black_in, white_in, ghosts_in, first_it, n, black_out, white_out, up, down);
 }
 
 int ising_row_ptr(ising_ctx* c, int dev, int color, int row, void** dptr, size_t* nbytes)

@@ -459,6 +459,22 @@ update_color_kernel(const __grid_constant__ CUtensorMap src_tile, const __grid_c
     }
 }
 
+// Wait until the neighbours' fused halo pushes have all arrived: flags[0], flags[2] (top / bottom ghost row
+// of colour 0) must have reached want0, flags[1], flags[3] want1.  Put on a stream ahead of anything that
+// overwrites the ghost rows (host upload of the next replica).
+__global__ void halo_wait_kernel(const unsigned int* flags, unsigned int want0, unsigned int want1)
+{
+    if (threadIdx.x < 4) {
+        const unsigned int want = (threadIdx.x & 1) ? want1 : want0;
+        while ((int)(ld_acquire_sys(flags + threadIdx.x) - want) < 0) { }
+    }
+}
+
+void launch_halo_wait(const unsigned int* flags, unsigned int want0, unsigned int want1, cudaStream_t stream)
+{
+    halo_wait_kernel<<<1, 32, 0, stream>>>(flags, want0, want1);
+}
+
 // (tiles_x, tile rows) as a 3-D grid: rows beyond 32768 spill into z
 static dim3 tile_grid(int tiles_x, int tile_rows)
 {

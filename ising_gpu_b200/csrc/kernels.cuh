@@ -99,6 +99,7 @@ void launch_bond_differ(const uint32_t* black, const uint32_t* white, int rows, 
                         int xperiod, uint32_t grow0, unsigned long long* counts, cudaStream_t stream);
 void launch_to_ref(const uint32_t* plane, int rows, int pitch, unsigned long long* out, cudaStream_t stream);
 void launch_from_ref(const unsigned long long* in, int rows, int pitch, uint32_t* plane, cudaStream_t stream);
+void launch_halo_wait(const unsigned int* flags, unsigned int want0, unsigned int want1, cudaStream_t stream);
 const char* update_kernel_name(int fast);
 
 }  // namespace ising

@@ -74,6 +74,8 @@ def load_library():
         "ising_run_from_host": ([vp, vp, vp, C.c_int, C.c_int, vp, vp, u64p, u64p], C.c_int),
         "ising_run_batch_from_host": ([vp, vp, C.c_int, C.POINTER(vp), C.POINTER(vp), C.c_int, C.c_int,
                                        C.POINTER(vp), C.POINTER(vp), u64p, u64p], C.c_int),
+        "ising_run_slab_batch_from_host": ([vp, vp, C.c_int, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.c_int, C.c_int,
+                                            C.POINTER(vp), C.POINTER(vp), u64p, u64p], C.c_int),
         "ising_row_ptr": ([vp, C.c_int, C.c_int, C.c_int, C.POINTER(vp), C.POINTER(C.c_size_t)], C.c_int),
         "ising_update_color_part": ([vp, C.c_int, C.c_int, C.c_int, C.c_int, vp], C.c_int),
         "ising_device_count": ([C.POINTER(C.c_int)], C.c_int),
@@ -116,7 +118,7 @@ EXPORTED_SYMBOLS = ("ising_create ising_destroy ising_last_error ising_abi_versi
                     "ising_set_temperature ising_count_spins ising_bond_sum ising_correlation "
                     "ising_export_bonds_ref_layout ising_export_ref_layout "
                     "ising_import_ref_layout ising_export_bits ising_import_bits ising_dump_lattice "
-                    "ising_run_from_host ising_run_batch_from_host ising_row_ptr ising_update_color_part ising_accept_count "
+                    "ising_run_from_host ising_run_batch_from_host ising_run_slab_batch_from_host ising_row_ptr ising_update_color_part ising_accept_count "
                     "ising_device_count ising_device_info ising_can_access_peer "
                     "ising_ipc_export ising_ipc_attach ising_push_edges "
                     "ising_accept_table ising_site_random ising_launch_count ising_kernel_name "
@@ -297,11 +299,13 @@ class IsingEngine:
         self.it += int(n)
         return int(up.value), int(dn.value)
 
-    def run_batch_from_host(self, other, black_in, white_in, n, black_out=None, white_out=None, first_it=1):
+    def run_batch_from_host(self, other, black_in, white_in, n, black_out=None, white_out=None, first_it=1,
+                            ghosts_in=None):
         """Replica batch (ising_run_batch_from_host): lattice k = (black_in[k], white_in[k]) is uploaded,
         evolved by n sweeps from iteration first_it, counted and downloaded; jobs alternate between this
         engine and `other` (same shape and device, or None) so copies overlap kernels.  Returns the
-        per-lattice (up, down) counts."""
+        per-lattice (up, down) counts.  With ghosts_in (slab contexts, fused halo) every rank passes its slab
+        of each replica plus its two white ghost rows (ising_run_slab_batch_from_host)."""
         k = len(black_in)
         assert len(white_in) == k
 
@@ -310,9 +314,15 @@ class IsingEngine:
                 return None
             return (C.c_void_p * k)(*[(a.ctypes.data if a is not None else None) for a in arrs])
         up, dn = (C.c_uint64 * k)(), (C.c_uint64 * k)()
-        self._ck(self._L.ising_run_batch_from_host(self._h, other._h if other is not None else None, k,
-                                                   ptrs(black_in), ptrs(white_in), int(first_it), int(n),
-                                                   ptrs(black_out), ptrs(white_out), up, dn))
+        oh = other._h if other is not None else None
+        if ghosts_in is None:
+            self._ck(self._L.ising_run_batch_from_host(self._h, oh, k, ptrs(black_in), ptrs(white_in), int(first_it),
+                                                       int(n), ptrs(black_out), ptrs(white_out), up, dn))
+        else:   # one slab of a multi-process lattice: ghosts_in[k] = (2, pitch) white rows above / below the slab
+            assert len(ghosts_in) == k and all(g.shape == (2, self.pitch) and g.dtype == np.uint32 for g in ghosts_in)
+            self._ck(self._L.ising_run_slab_batch_from_host(self._h, oh, k, ptrs(black_in), ptrs(white_in),
+                                                            ptrs(ghosts_in), int(first_it), int(n), ptrs(black_out),
+                                                            ptrs(white_out), up, dn))
         return [(int(up[i]), int(dn[i])) for i in range(k)]
 
     def ipc_export(self):

@@ -160,6 +160,25 @@ class SlabEngine:
         if self.world > 1 and self.overlap:
             self.main.wait_event(self._ev_comm)
 
+    def white_ghost_rows(self):
+        """The two white ghost rows (above, below the slab) as a (2, X/64) uint32 host array: what
+        ising_run_slab_batch_from_host wants next to a slab uploaded from the host."""
+        import numpy as np
+        torch.cuda.synchronize()
+        top, bottom = self.slab.ghost_rows(1)
+        return np.stack([top.cpu().numpy(), bottom.cpu().numpy()]).view(np.uint32)
+
+    def run_batch_from_host(self, other, black_in, white_in, ghosts_in, n, black_out=None, white_out=None):
+        """Replica batch on this rank's slab (see IsingEngine.run_batch_from_host); `other` is a second
+        SlabEngine of the same shape on the same GPU.  Every rank of the group must make the same call."""
+        if self.world == 1:
+            return self.eng.run_batch_from_host(other.eng if other else None, black_in, white_in, n, black_out, white_out,
+                                                first_it=self.it + 1)
+        if not self.fused:
+            raise ValueError("replica batches over several slabs need halo='fused'")
+        return self.eng.run_batch_from_host(other.eng if other else None, black_in, white_in, n, black_out, white_out,
+                                            first_it=self.it + 1, ghosts_in=ghosts_in)
+
     def count_spins(self):
         return self.eng.count_spins()
 

@@ -146,3 +146,18 @@ def test_more_than_65535_tile_rows(ig):
     assert sum(e.count_spins()[0] for e in engs) == cnt[0]
     for e in engs:
         e.close()
+
+
+def test_slab_replica_batch(tmp_path):
+    """torchrun, 2 ranks x 2 contexts: ising_run_slab_batch_from_host (5 different replicas, host ghosts,
+    fused halo between the ranks, copies overlapping kernels) == the plain import/refresh/sweeps/export path."""
+    if _ngpu() < 2:
+        pytest.skip("needs 2 GPUs")
+    out = tmp_path / "batch"
+    out.mkdir()
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr",
+           "127.0.0.1", "--master-port", "29534", os.path.join(ROOT, "tests", "slab_batch_worker.py"), "4096", "128",
+           "4", "5", str(out)]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert [(out / ("ok%d" % k)).read_text() for k in range(2)] == ["1", "1"]
