@@ -193,6 +193,23 @@ def run_b200(a):
             t = torch.empty((rows, pitch), dtype=torch.int32).pin_memory()
             return t, t.numpy().view(np.uint32)
         b0, w0 = eng.eng.export_bits()
+
+        def plain_e2e(nb, nw):
+            """One step after the other, nothing overlapped (the transport-agnostic path; also the fallback)."""
+            def e2e_step():
+                eng.eng.import_bits(nb, nw)          # H2D of both colour planes (pinned)
+                eng.refresh_ghosts()                  # ghost rows belong to the uploaded state
+                eng.sweeps(S)
+                eng.eng._ck(eng.eng._L.ising_export_bits(eng.eng._h, 0, nb.ctypes.data, nw.ctypes.data))  # D2H
+                return eng.count_spins()              # D2H of the step's observable
+            e2e_step()
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(ksteps):
+                e2e_step()
+            barrier()
+            return time.perf_counter() - t0
+
         if world == 1:
             # replica batch: every step is one job of the batch = upload both planes of a lattice from
             # pinned memory, S sweeps, spin counts, download both planes; jobs alternate between two
@@ -265,40 +282,33 @@ def run_b200(a):
             counts = batch(ksteps)
             barrier()
             dt = time.perf_counter() - t0
-            assert all(c == want_counts for c in counts), (counts, want_counts)
-            for ob, ow in outs[:min(2, ksteps)]:
-                assert np.array_equal(ob, want_b) and np.array_equal(ow, want_w), "pipelined slab batch differs"
+            ok = all(c == want_counts for c in counts) and all(
+                np.array_equal(ob, want_b) and np.array_equal(ow, want_w) for ob, ow in outs[:min(2, ksteps)])
             del want_b, want_w
-            t = torch.tensor([dt], device="cuda", dtype=torch.float64)
+            t = torch.tensor([dt, -float(ok)], device="cuda", dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            dt = float(t.item())
+            dt, ok = float(t[0].item()), float(t[1].item()) == -1.0      # ok on every rank
             eng2.close()
             api = ("ising_run_slab_batch_from_host (C ABI, pinned host buffers): per step and rank H2D of the slab's planes "
                    "and white ghost rows, %d sweeps with the fused halo push, count kernels, D2H of planes and counts; "
-                   "two contexts per rank, copies overlap the other step's kernels" % S)
+                   "two contexts per rank, copies overlap the other step's kernels; result checked against the "
+                   "unpipelined path" % S)
+            if not ok:   # never report a number for a wrong result: measure the plain path instead and say so
+                dt = plain_e2e(ins[0][0], ins[0][1])
+                t = torch.tensor([dt], device="cuda", dtype=torch.float64)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                dt = float(t.item())
+                api = ("PIPELINED RESULT MISMATCH, fell back to ising_import_bits + ising_sweeps + ising_export_bits + "
+                       "ising_count_spins per step, not pipelined")
         else:
             (hb, nb), (hw, nw) = pinned(), pinned()
             nb[:], nw[:] = b0, w0
             del b0, w0
-
-            def e2e_step():
-                eng.eng.import_bits(nb, nw)          # H2D of both colour planes (pinned)
-                eng.refresh_ghosts()                  # ghost rows belong to the uploaded state
-                eng.sweeps(S)
-                eng.eng._ck(eng.eng._L.ising_export_bits(eng.eng._h, 0, nb.ctypes.data, nw.ctypes.data))  # D2H
-                return eng.count_spins()              # D2H of the step's observable
-
-            e2e_step()
-            barrier()
-            t0 = time.perf_counter()
-            for _ in range(ksteps):
-                e2e_step()
-            barrier()
-            dt = time.perf_counter() - t0
+            dt = plain_e2e(nb, nw)
             t = torch.tensor([dt], device="cuda", dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             dt = float(t.item())
-            api = ("ising_import_bits + ising_sweeps (fused halo) + ising_export_bits + ising_count_spins per step "
+            api = ("ising_import_bits + ising_sweeps + ising_export_bits + ising_count_spins per step "
                    "(C ABI, pinned host buffers), not pipelined")
         e2e = {"value": round(float(X_COLS) * rows * S * ksteps * world / (dt * 1e9), 2), "unit": "flips/ns",
                "h2d_bytes_per_step": (2 * plane_bytes + (2 * pitch * 4 if world > 1 and a.halo == "fused" else 0)) * world, "d2h_bytes_per_step": (2 * plane_bytes + 8) * world,
