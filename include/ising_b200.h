@@ -140,6 +140,13 @@ int ising_import_ref_layout(ising_ctx* ctx, int dev, const uint64_t* black, cons
 /* Device packing: Y*X/64 uint32 words per colour, bit b of word w = colour-column 32*w+b. */
 int ising_export_bits(ising_ctx* ctx, int dev, uint32_t* black, uint32_t* white);
 int ising_import_bits(ising_ctx* ctx, int dev, const uint32_t* black, const uint32_t* white);
+/* Binary checkpoint of every device of the context (the reference has none): a header
+ * (shape, slabs, seed, temperature, sweeps done) and the bit-packed colour planes.  Loading checks the
+ * shape and the seed -- the continuation draws from the same Philox stream, so `n1` sweeps, save,
+ * load, `n2` sweeps starting at iteration n1 + 1 equal n1 + n2 sweeps -- and refreshes the ghost rows
+ * between the context's own devices.  iterations_done may be NULL. */
+int ising_save_checkpoint(ising_ctx* ctx, const char* path, uint64_t iterations_done);
+int ising_load_checkpoint(ising_ctx* ctx, const char* path, uint64_t* iterations_done);
 /* dumpLattice (main.cu:1140-1209): writes "<prefix><dev>.txt" for every device of the context. */
 int ising_dump_lattice(ising_ctx* ctx, const char* prefix);
 

@@ -102,7 +102,14 @@ constexpr int MAX_CORR_LEN = 128;            // main.cu:70
            "\t\tlattice per  GPU  (specified  with  the  '-y'  option) and a multiple of %d.\n\n"
            "\t-o|--o\n"
            "\t\tEnables the file dump of  the lattice  every time  the magnetization is printed.\n"
-           "\t\tDefault: off\n\n",
+           "\t\tDefault: off\n\n"
+           "Options not in the reference:\n"
+           "\t   --save <FILE>\n"
+           "\t\tWrites a binary checkpoint (bit-packed lattice of all GPUs, seed,  iterations)\n"
+           "\t\tat the end of the run.\n\n"
+           "\t   --load <FILE>\n"
+           "\t\tStarts from a checkpoint instead of the random lattice; iteration numbers -- and\n"
+           "\t\ttherefore the random numbers -- continue where the saved run stopped.\n\n",
            bname, X_MULT, Y_MULT, 1, (unsigned long long)ISING_DEFAULT_SEED, ALPHA_DEF,
            ALPHA_DEF * ISING_CRIT_TEMP, MAX_CORR_LEN, X_MULT, Y_MULT);
     exit(EXIT_SUCCESS);   // the reference's usage() always exits with success (main.cu:828)
@@ -128,6 +135,7 @@ std::vector<unsigned long long> exp_series(unsigned long long nsteps)
 int main(int argc, char** argv)
 {
     int X = 0, Y = 0, dumpOut = 0, corrOut = 0, nsteps = 1, ndev = 1;
+    const char *ckptSave = nullptr, *ckptLoad = nullptr;
     unsigned long long seed = ISING_DEFAULT_SEED;
     float alpha = -1.0f, temp = -1.0f, tempUpdStep = 0;
     int tempUpdFreq = 0, printFreq = 0, printExp = 0, printExpCur = 0;
@@ -146,6 +154,7 @@ int main(int argc, char** argv)
         {"magn", required_argument, 0, 'm'},  {"exppr", no_argument, 0, 'e'},
         {"corr", no_argument, 0, 'c'},        {"J", required_argument, 0, 'J'},
         {"xsl", required_argument, 0, 1},     {"ysl", required_argument, 0, 2},
+        {"save", required_argument, 0, 3},    {"load", required_argument, 0, 4},   // checkpoint (not in the reference)
         {"help", required_argument, 0, 'h'},  {0, 0, 0, 0}};
 
     for (;;) {
@@ -187,6 +196,8 @@ int main(int argc, char** argv)
                 break;
             case 1: useSubLatt = 1; XSL = atoi(optarg); break;
             case 2: useSubLatt = 1; YSL = atoi(optarg); break;
+            case 3: ckptSave = optarg; break;
+            case 4: ckptLoad = optarg; break;
             case '?': exit(EXIT_FAILURE);
             default: fprintf(stderr, "unknown option: %c\n", och); exit(EXIT_FAILURE);
         }
@@ -312,6 +323,11 @@ int main(int argc, char** argv)
     ISING_CALL(ising_create(&cfg, &ctx));
 
     ISING_CALL(ising_init_lattice(ctx));
+    uint64_t it0 = 0;                       // sweeps already done by the run a checkpoint comes from
+    if (ckptLoad) {
+        ISING_CALL(ising_load_checkpoint(ctx, ckptLoad, &it0));
+        printf("\nLoaded checkpoint %s (%llu iterations done)\n", ckptLoad, (unsigned long long)it0);
+    }
     uint64_t cntPos = 0, cntNeg = 0;
     ISING_CALL(ising_count_spins(ctx, &cntPos, &cntNeg));
     printf("\nInitial magnetization: %9.6lf, up_s: %12llu, dw_s: %12llu\n",
@@ -345,7 +361,7 @@ int main(int argc, char** argv)
     const auto t0 = std::chrono::steady_clock::now();
     int j;
     for (j = 0; j < nsteps; j++) {
-        ISING_CALL(ising_sweeps(ctx, j + 1, 1));
+        ISING_CALL(ising_sweeps(ctx, (int)it0 + j + 1, 1));
         const bool atFreq = printFreq && ((j + 1) % printFreq) == 0;
         const bool atExp = printExp && printExpSteps[printExpCur] == (unsigned long long)j;
         bool stop = false;
@@ -395,6 +411,10 @@ int main(int argc, char** argv)
            (double)nspins * j / (et * 1.0E+6), (2.0 * j * bytes_per_color / 1.0E+9) / (et / 1.0E+3));
 
     if (dumpOut) dump(j);
+    if (ckptSave) {
+        ISING_CALL(ising_save_checkpoint(ctx, ckptSave, it0 + (uint64_t)j));
+        printf("Saved checkpoint %s (%llu iterations done)\n", ckptSave, (unsigned long long)(it0 + j));
+    }
     ISING_CALL(ising_destroy(ctx));
     return 0;
 }

@@ -742,6 +742,80 @@ int ising_import_bits(ising_ctx* c, int dev, const uint32_t* black, const uint32
     return refresh_ghosts_after_import(c);
 }
 
+// ---- binary checkpoint (the reference has none) ---------------------------------
+namespace {
+struct CkptHeader {
+    char magic[8];          // "ISB200CK"
+    uint32_t version;       // 1
+    int32_t X, Y, ndev, xsl, ysl, slab_first, slab_count;
+    uint64_t seed;
+    float temp;
+    uint32_t pad;
+    uint64_t iterations;    // sweeps done; the next sweep uses it = iterations + 1
+};
+}  // namespace
+
+int ising_save_checkpoint(ising_ctx* c, const char* path, uint64_t iterations_done)
+{
+    if (!c || !path) return fail(ISING_EINVAL, "bad argument");
+    FILE* fp = fopen(path, "wb");
+    if (!fp) return fail(ISING_EINVAL, "cannot open %s for writing", path);
+    CkptHeader h{};
+    memcpy(h.magic, "ISB200CK", 8);
+    h.version = 1;
+    h.X = c->cfg.X; h.Y = c->cfg.Y; h.ndev = (int32_t)c->dev.size(); h.xsl = c->cfg.xsl; h.ysl = c->cfg.ysl;
+    h.slab_first = c->cfg.slab_first; h.slab_count = c->slab_count; h.seed = c->cfg.seed; h.temp = c->cfg.temp;
+    h.iterations = iterations_done;
+    const size_t words = (size_t)c->cfg.Y * c->pitch;
+    std::vector<uint32_t> b(words), w(words);
+    bool ok = fwrite(&h, sizeof(h), 1, fp) == 1;
+    for (int i = 0; ok && i < (int)c->dev.size(); i++) {
+        if (int rc = ising_export_bits(c, i, b.data(), w.data())) { fclose(fp); return rc; }
+        ok = fwrite(b.data(), 4, words, fp) == words && fwrite(w.data(), 4, words, fp) == words;
+    }
+    ok = (fclose(fp) == 0) && ok;
+    return ok ? ISING_OK : fail(ISING_EINVAL, "short write to %s", path);
+}
+
+int ising_load_checkpoint(ising_ctx* c, const char* path, uint64_t* iterations_done)
+{
+    if (!c || !path) return fail(ISING_EINVAL, "bad argument");
+    FILE* fp = fopen(path, "rb");
+    if (!fp) return fail(ISING_EINVAL, "cannot open %s", path);
+    CkptHeader h{};
+    if (fread(&h, sizeof(h), 1, fp) != 1 || memcmp(h.magic, "ISB200CK", 8) != 0 || h.version != 1) {
+        fclose(fp);
+        return fail(ISING_EINVAL, "%s is not an ising_b200 checkpoint", path);
+    }
+    if (h.X != c->cfg.X || h.Y != c->cfg.Y || h.ndev != (int32_t)c->dev.size() || h.slab_first != c->cfg.slab_first ||
+        h.slab_count != c->slab_count || h.xsl != c->cfg.xsl || h.ysl != c->cfg.ysl) {
+        fclose(fp);
+        return fail(ISING_EINVAL, "checkpoint %s is %d x %d x %d devices (slabs %d+%d, sub-lattice %d x %d): does not match this context",
+                    path, h.Y, h.X, h.ndev, h.slab_first, h.slab_count, h.ysl, h.xsl);
+    }
+    if (h.seed != c->cfg.seed) {   // the random-number stream of the continuation depends on it
+        fclose(fp);
+        return fail(ISING_EINVAL, "checkpoint %s was written with seed %llu, this context uses %llu", path,
+                    (unsigned long long)h.seed, (unsigned long long)c->cfg.seed);
+    }
+    const size_t words = (size_t)c->cfg.Y * c->pitch;
+    std::vector<uint32_t> b(words), w(words);
+    for (int i = 0; i < (int)c->dev.size(); i++) {
+        if (fread(b.data(), 4, words, fp) != words || fread(w.data(), 4, words, fp) != words) {
+            fclose(fp);
+            return fail(ISING_EINVAL, "checkpoint %s is truncated", path);
+        }
+        DevState& d = c->dev[i];
+        CU_TRY(cudaSetDevice(d.device));
+        CU_TRY(cudaMemcpyAsync(local_row(c, d, 0, 0), b.data(), words * 4, cudaMemcpyHostToDevice, d.stream));
+        CU_TRY(cudaMemcpyAsync(local_row(c, d, 1, 0), w.data(), words * 4, cudaMemcpyHostToDevice, d.stream));
+        CU_TRY(cudaStreamSynchronize(d.stream));
+    }
+    fclose(fp);
+    if (iterations_done) *iterations_done = h.iterations;
+    return refresh_ghosts_after_import(c);   // all devices are loaded: boundary rows -> neighbours' ghost rows
+}
+
 int ising_export_ref_layout(ising_ctx* c, int dev, uint64_t* black, uint64_t* white)
 {
     if (int rc = check_dev(c, dev)) return rc;

@@ -71,6 +71,8 @@ def load_library():
         "ising_export_bits": ([vp, C.c_int, vp, vp], C.c_int),
         "ising_import_bits": ([vp, C.c_int, vp, vp], C.c_int),
         "ising_dump_lattice": ([vp, C.c_char_p], C.c_int),
+        "ising_save_checkpoint": ([vp, C.c_char_p, C.c_uint64], C.c_int),
+        "ising_load_checkpoint": ([vp, C.c_char_p, u64p], C.c_int),
         "ising_run_from_host": ([vp, vp, vp, C.c_int, C.c_int, vp, vp, u64p, u64p], C.c_int),
         "ising_run_batch_from_host": ([vp, vp, C.c_int, C.POINTER(vp), C.POINTER(vp), C.c_int, C.c_int,
                                        C.POINTER(vp), C.POINTER(vp), u64p, u64p], C.c_int),
@@ -118,6 +120,7 @@ EXPORTED_SYMBOLS = ("ising_create ising_destroy ising_last_error ising_abi_versi
                     "ising_set_temperature ising_count_spins ising_bond_sum ising_correlation "
                     "ising_export_bonds_ref_layout ising_export_ref_layout "
                     "ising_import_ref_layout ising_export_bits ising_import_bits ising_dump_lattice "
+                    "ising_save_checkpoint ising_load_checkpoint "
                     "ising_run_from_host ising_run_batch_from_host ising_run_slab_batch_from_host ising_row_ptr ising_update_color_part ising_accept_count "
                     "ising_device_count ising_device_info ising_can_access_peer "
                     "ising_ipc_export ising_ipc_attach ising_push_edges "
@@ -290,6 +293,15 @@ class IsingEngine:
 
     def dump_lattice(self, prefix):
         self._ck(self._L.ising_dump_lattice(self._h, os.fsencode(prefix)))
+
+    def save_checkpoint(self, path):
+        self._ck(self._L.ising_save_checkpoint(self._h, os.fsencode(path), self.it))
+
+    def load_checkpoint(self, path):
+        it = C.c_uint64()
+        self._ck(self._L.ising_load_checkpoint(self._h, os.fsencode(path), C.byref(it)))
+        self.it = int(it.value)
+        return self.it
 
     def run_from_host(self, black_in, white_in, n, black_out, white_out, counts=True):
         up, dn = C.c_uint64(), C.c_uint64()

@@ -36,3 +36,25 @@ def test_cli_matches_reference_transcript(case, tmp_path):
 def test_cli_bad_dims_prints_usage_and_exits_zero(tmp_path):
     r = subprocess.run([CLI, "-x", "100"], cwd=tmp_path, capture_output=True, text=True)
     assert r.returncode == 0 and "Please specify an X dim multiple of 2048" in r.stderr and "Usage:" in r.stdout
+
+
+def test_cli_checkpoint_save_load_continues_the_run(tmp_path):
+    """cuIsing -n 3 --save + cuIsing -n 4 --load == cuIsing -n 7 (final counts and dump); the reference has no
+    checkpoint, so the golden is the uninterrupted run of the same program (itself pinned above)."""
+    base = ["-x", "4096", "-y", "64", "-t", "2.269185"]
+
+    def final(args, cwd):
+        os.makedirs(cwd, exist_ok=True)
+        r = subprocess.run([CLI] + base + args, cwd=cwd, capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stderr[-1000:]
+        return [ln.split("(iter")[0] for ln in r.stdout.splitlines() if ln.startswith("Final")][0]
+    whole = final(["-n", "7", "-o"], tmp_path / "whole")
+    ck = str(tmp_path / "state.ckpt")
+    final(["-n", "3", "--save", ck], tmp_path / "part1")
+    cont = final(["-n", "4", "--load", ck, "-o"], tmp_path / "part2")
+    assert cont == whole
+    # the continued run numbers its own iterations from 1: compare the lattice dumps by content
+    d1 = [p for p in os.listdir(tmp_path / "whole") if p.startswith("lattice_")]
+    d2 = [p for p in os.listdir(tmp_path / "part2") if p.startswith("lattice_")]
+    assert len(d1) == 1 and len(d2) == 1
+    assert open(tmp_path / "whole" / d1[0], "rb").read() == open(tmp_path / "part2" / d2[0], "rb").read()

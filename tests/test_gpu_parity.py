@@ -152,3 +152,27 @@ def test_replica_batch_from_host_matches_oracle(ig, oracle):
                 assert counts[k] == wc
         # outputs and counts are optional
         assert ea.run_batch_from_host(eb, [starts[0][0]], [starts[0][1]], n) == [want[0][2]]
+
+
+def test_checkpoint_continues_the_run(ig, oracle, tmp_path):
+    """n1 sweeps, save, load into a fresh context, n2 sweeps == n1 + n2 sweeps (same Philox stream);
+    shape / seed mismatches and foreign files are refused."""
+    X, Y, n1, n2 = 4096, 48, 3, 4
+    ck = str(tmp_path / "run.ckpt")
+    with ig.IsingEngine(X, Y, temp=TC) as eng:
+        eng.init_lattice(); eng.sweeps(n1)
+        eng.save_checkpoint(ck)
+    ora = oracle.OracleLattice(X, Y)
+    ora.init(); ora.sweeps(n1 + n2, TC)
+    with ig.IsingEngine(X, Y, temp=TC) as eng:
+        assert eng.load_checkpoint(ck) == n1
+        eng.sweeps(n2)
+        _compare(eng, ora, "continued run")
+    with ig.IsingEngine(X, Y + 16, temp=TC) as eng, pytest.raises(ig.IsingError, match="does not match"):
+        eng.load_checkpoint(ck)
+    with ig.IsingEngine(X, Y, temp=TC, seed=7) as eng, pytest.raises(ig.IsingError, match="seed"):
+        eng.load_checkpoint(ck)
+    bad = tmp_path / "bad.ckpt"
+    bad.write_bytes(b"not a checkpoint" * 8)
+    with ig.IsingEngine(X, Y, temp=TC) as eng, pytest.raises(ig.IsingError, match="not an ising_b200 checkpoint"):
+        eng.load_checkpoint(str(bad))
