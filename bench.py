@@ -115,6 +115,17 @@ def ncu_traffic_per_launch():
         return None
 
 
+def ncu_pipe_summary():
+    """What actually binds the kernel (committed ncu capture): busiest pipe and issue-slot use, or None."""
+    p = os.path.join(ROOT, "profiles", "update_kernel_ncu_summary.json")
+    try:
+        d = json.load(open(p))
+        return {"fmaheavy_pipe_pct": round(float(d["pipe_fmaheavy_pct"]), 1), "alu_pipe_pct": round(float(d["pipe_alu_pct"]), 1),
+                "issue_slots_pct": round(float(d["issue_active_pct"]), 1), "source": "profiles/update_kernel_ncu_summary.json"}
+    except Exception:
+        return None
+
+
 def cpu_baselines():
     from oracle import ising_oracle, numpy_basic
     n = 4096
@@ -340,6 +351,7 @@ def run_b200(a):
                 "kernel": eng.eng.kernel_name, "kernel_ms": round(kern_ms, 4),
                 "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
                 "reference_accounting_gbs": round(achieved * REF_BYTES_PER_FLIP / ALG_BYTES_PER_FLIP, 1),
+                "binding_resource": ncu_pipe_summary(),
                 "note": "HBM-nominal path, but the bit-exact Philox4x32-10 per site makes it bound by the "
                         "FMA-heavy pipe (IMAD.WIDE, 4 cycles/warp-instr): see DESIGN.md and profiles/"}
         out = {"metric": "spin-flip attempts/ns", "value": round(value, 2), "unit": "flips/ns", "n_gpus": world,
