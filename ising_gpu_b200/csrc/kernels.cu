@@ -54,20 +54,6 @@ __device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int* p)
     return v;
 }
 
-// acc = 2*acc + (x > thr): x + ~thr carries out of 32 bits exactly when x > thr; the carry
-// flag is shifted in by the add-with-carry (IADD3 + IADD3.X / IMAD.X in SASS).  Rejected
-// sites accumulate as 1 bits.  nthr = ~thr.
-__device__ __forceinline__ void shift_in_reject(uint32_t& acc, uint32_t x, uint32_t nthr)
-{
-    asm("{\n"
-        ".reg .u32 t;\n"
-        "add.cc.u32 t, %1, %2;\n"
-        "addc.u32 %0, %0, %0;\n"
-        "}\n"
-        : "+r"(acc)
-        : "r"(x), "r"(nthr));
-}
-
 // acc |= (x > thr) << BIT as one compare and one predicated OR-immediate.
 __device__ __forceinline__ void or_bit_if_gt(uint32_t& acc, uint32_t x, uint32_t thr, int bit)
 {
@@ -78,18 +64,6 @@ __device__ __forceinline__ void or_bit_if_gt(uint32_t& acc, uint32_t x, uint32_t
         "}\n"
         : "+r"(acc)
         : "r"(x), "r"(thr), "r"(1u << bit));   // bit is a literal after unrolling
-}
-
-// acc += 2^bit if x > thr, in FP32 (exact: acc < 2^24).
-__device__ __forceinline__ void fadd_bit_if_gt(float& acc, uint32_t x, uint32_t thr, int bit)
-{
-    asm("{\n"
-        ".reg .pred p;\n"
-        "setp.gt.u32 p, %1, %2;\n"
-        "@p add.f32 %0, %0, %3;\n"
-        "}\n"
-        : "+f"(acc)
-        : "r"(x), "r"(thr), "f"((float)(1u << bit)));
 }
 
 // Which multiplies of call q (0..7 inside a word) take the FP64 route of philox_map.h: bit q of
@@ -110,55 +84,16 @@ __device__ __forceinline__ void philox_call(int q, const ThreadConsts& tc, uint3
     else           philox_fast(tc, ta, tb, td, k0, k1, out);
 }
 
-// acc |= (x > thr) << BIT with the compare on the FP64 pipe: xd = 2^52 + x, thrd = 2^52 + thr.
-__device__ __forceinline__ void or_bit_if_gt_f64(uint32_t& acc, double xd, double thrd, int bit)
-{
-    asm("{\n"
-        ".reg .pred p;\n"
-        "setp.gt.f64 p, %1, %2;\n"
-        "@p or.b32 %0, %0, %3;\n"
-        "}\n"
-        : "+r"(acc)
-        : "d"(xd), "d"(thrd), "r"(1u << bit));
-}
-
 // Reject masks of one 32-site word: 8 Philox calls, outputs x,y,z,w -> bits 2q, 16+2q, 2q+1,
-// 17+2q.
-#ifndef ISING_ACC_VARIANT
-#define ISING_ACC_VARIANT 1
-#endif
-#ifndef ISING_CARRY_CALLS
-#define ISING_CARRY_CALLS 2
-#endif
+// 17+2q.  One compare + one predicated add of the site's bit per threshold (ISETP on the ALU
+// pipe, VIADD on the FMA pipe).  Measured alternatives, all bit-exact and none faster (numbers in
+// profiles/r01_occupancy_variants.txt): carry-chain accumulation
+// (IADD3 + IADD3.X), predicated LOP3, FP32 accumulators on the FMA-lite pipe, a mix of these,
+// and compares on the FP64 pipe (DSETP).
 template <int NTHR, int J>
 __device__ __forceinline__ void word_reject_masks(const ThreadConsts& tc, const StepTables& st, uint32_t thrA,
-                                                  uint32_t thrB, uint32_t zero, uint32_t& rejA, uint32_t& rejB)
+                                                  uint32_t thrB, uint32_t& rejA, uint32_t& rejB)
 {
-#if ISING_ACC_VARIANT == 0
-    // carry chain: calls run q = 7..0 so that shifting in z then x (w then y) leaves bit k of
-    // the 16-bit accumulators == site k
-    const uint32_t nA = ~thrA, nB = ~thrB;
-    uint32_t a_lo = 0, a_hi = 0, b_lo = 0, b_hi = 0;
-#pragma unroll
-    for (int q = 7; q >= 0; q--) {
-        const int cl = 8 * J + q;
-        uint32_t o[4];
-        philox_call(q, tc, st.a[cl], st.b[cl], st.d[cl], st.k0, st.k1, o);
-        shift_in_reject(a_lo, o[2], nA);
-        shift_in_reject(a_lo, o[0], nA);
-        shift_in_reject(a_hi, o[3], nA);
-        shift_in_reject(a_hi, o[1], nA);
-        if (NTHR > 1) {
-            shift_in_reject(b_lo, o[2], nB);
-            shift_in_reject(b_lo, o[0], nB);
-            shift_in_reject(b_hi, o[3], nB);
-            shift_in_reject(b_hi, o[1], nB);
-        }
-    }
-    rejA = __byte_perm(a_lo, a_hi, 0x5410);
-    rejB = (NTHR > 1) ? __byte_perm(b_lo, b_hi, 0x5410) : 0u;
-#elif ISING_ACC_VARIANT == 1
-    // compare + predicated OR of the site's bit: ISETP + @P LOP3, both on the ALU pipe
     uint32_t a = 0, b = 0;
 #pragma unroll
     for (int q = 0; q < 8; q++) {
@@ -178,98 +113,6 @@ __device__ __forceinline__ void word_reject_masks(const ThreadConsts& tc, const 
     }
     rejA = a;
     rejB = b;
-#elif ISING_ACC_VARIANT == 4
-    // as variant 1, but the two outputs that end a round as the low word of an FP64-pipe result
-    // (x and z) are compared on the FP64 pipe (DSETP), the other two on the ALU (ISETP)
-    uint32_t a = 0, b = 0;
-    const double tAd = __hiloint2double((int)DBL_2P52_HI, (int)thrA), tBd = __hiloint2double((int)DBL_2P52_HI, (int)thrB);
-#pragma unroll
-    for (int q = 0; q < 8; q++) {
-        const int cl = 8 * J + q;
-        uint32_t o[4];
-        double d0, d2;
-        philox_fast_mix<false, false>(tc, st.a[cl], st.b[cl], st.d[cl], st.k0, st.k1, o, &d0, &d2);
-        or_bit_if_gt_f64(a, d0, tAd, 2 * q);
-        or_bit_if_gt(a, o[1], thrA, 16 + 2 * q);
-        or_bit_if_gt_f64(a, d2, tAd, 2 * q + 1);
-        or_bit_if_gt(a, o[3], thrA, 17 + 2 * q);
-        if (NTHR > 1) {
-            or_bit_if_gt_f64(b, d0, tBd, 2 * q);
-            or_bit_if_gt(b, o[1], thrB, 16 + 2 * q);
-            or_bit_if_gt_f64(b, d2, tBd, 2 * q + 1);
-            or_bit_if_gt(b, o[3], thrB, 17 + 2 * q);
-        }
-    }
-    rejA = a;
-    rejB = b;
-#elif ISING_ACC_VARIANT == 2
-    // FP32 accumulators (predicated FADD of 2^k): measured no faster -- FMA-lite shares its
-    // dispatch with FMA-heavy, so the FADDs still compete with the IMAD.WIDEs.
-    float a_lo = 8388608.0f, a_hi = 8388608.0f, b_lo = 8388608.0f, b_hi = 8388608.0f;
-#pragma unroll
-    for (int q = 0; q < 8; q++) {
-        const int cl = 8 * J + q;
-        uint32_t o[4];
-        philox_call(q, tc, st.a[cl], st.b[cl], st.d[cl], st.k0, st.k1, o);
-        fadd_bit_if_gt(a_lo, o[0], thrA, 2 * q);
-        fadd_bit_if_gt(a_hi, o[1], thrA, 2 * q);
-        fadd_bit_if_gt(a_lo, o[2], thrA, 2 * q + 1);
-        fadd_bit_if_gt(a_hi, o[3], thrA, 2 * q + 1);
-        if (NTHR > 1) {
-            fadd_bit_if_gt(b_lo, o[0], thrB, 2 * q);
-            fadd_bit_if_gt(b_hi, o[1], thrB, 2 * q);
-            fadd_bit_if_gt(b_lo, o[2], thrB, 2 * q + 1);
-            fadd_bit_if_gt(b_hi, o[3], thrB, 2 * q + 1);
-        }
-    }
-    rejA = __byte_perm(__float_as_uint(a_lo), __float_as_uint(a_hi), 0x5410);
-    rejB = (NTHR > 1) ? __byte_perm(__float_as_uint(b_lo), __float_as_uint(b_hi), 0x5410) : 0u;
-#else
-    // Pipe-balanced form (pipe map measured on B200 with tools/pipe_map.cu): the FMA pipe is
-    // held 4 cycles by every IMAD.WIDE and is the binding resource; the ALU pipe carries the
-    // Philox XORs and the compares.  The masks of the top ISING_CARRY_CALLS calls are built
-    // with the carry chain (compare on ALU, shift-in as IMAD.X on FMA), the rest with compare +
-    // predicated OR (both ALU), which levels the two pipes.
-    constexpr int NC = ISING_CARRY_CALLS;
-    const uint32_t nA = ~thrA, nB = ~thrB;
-    uint32_t a = zero, b = zero;                        // `zero` is a run-time 0: keeps the ORs LOP3
-    uint32_t ca_lo = 0, ca_hi = 0, cb_lo = 0, cb_hi = 0;  // carry-chain accumulators, sites 16-2NC..15
-#pragma unroll
-    for (int q = 7; q >= 0; q--) {
-        const int cl = 8 * J + q;
-        uint32_t o[4];
-        philox_call(q, tc, st.a[cl], st.b[cl], st.d[cl], st.k0, st.k1, o);
-        if (q >= 8 - NC) {
-            shift_in_reject(ca_lo, o[2], nA);
-            shift_in_reject(ca_lo, o[0], nA);
-            shift_in_reject(ca_hi, o[3], nA);
-            shift_in_reject(ca_hi, o[1], nA);
-            if (NTHR > 1) {
-                shift_in_reject(cb_lo, o[2], nB);
-                shift_in_reject(cb_lo, o[0], nB);
-                shift_in_reject(cb_hi, o[3], nB);
-                shift_in_reject(cb_hi, o[1], nB);
-            }
-        } else {
-            or_bit_if_gt(a, o[0], thrA, 2 * q);
-            or_bit_if_gt(a, o[1], thrA, 16 + 2 * q);
-            or_bit_if_gt(a, o[2], thrA, 2 * q + 1);
-            or_bit_if_gt(a, o[3], thrA, 17 + 2 * q);
-            if (NTHR > 1) {
-                or_bit_if_gt(b, o[0], thrB, 2 * q);
-                or_bit_if_gt(b, o[1], thrB, 16 + 2 * q);
-                or_bit_if_gt(b, o[2], thrB, 2 * q + 1);
-                or_bit_if_gt(b, o[3], thrB, 17 + 2 * q);
-            }
-        }
-    }
-    if (NC > 0) {   // the chain masks cover sites 16-2NC..15 of each half
-        a |= (ca_lo << ((16 - 2 * NC) & 31)) | (ca_hi << ((32 - 2 * NC) & 31));
-        b |= (cb_lo << ((16 - 2 * NC) & 31)) | (cb_hi << ((32 - 2 * NC) & 31));
-    }
-    rejA = a;
-    rejB = b;
-#endif
 }
 
 // Flip mask of one word from its own spins, the four neighbour words and the reject masks.
@@ -308,9 +151,6 @@ __device__ __forceinline__ uint32_t flip_mask(uint32_t me, uint32_t up, uint32_t
 #ifndef ISING_MIN_BLOCKS
 #define ISING_MIN_BLOCKS 4
 #endif
-#ifndef ISING_PROLOGUE
-#define ISING_PROLOGUE 2
-#endif
 template <bool FAST, bool BONDS, bool PUSH>
 __global__ void __launch_bounds__(UPDATE_THREADS, ISING_MIN_BLOCKS)
 update_color_kernel(const __grid_constant__ CUtensorMap src_tile, const __grid_constant__ CUtensorMap src_row,
@@ -337,10 +177,6 @@ update_color_kernel(const __grid_constant__ CUtensorMap src_tile, const __grid_c
     // own spins: two 32-site words per thread, in flight while the random numbers are made
     uint32_t* const my = dst + (size_t)(y0 + ty) * p.pitch + x0 + tx;
     uint32_t me[2];
-#if ISING_PROLOGUE == 0
-    me[0] = my[0];
-    me[1] = my[16];
-#endif
     // +-J bonds of the thread's sites (main.cu:575-618): one bit plane per direction
     uint32_t jb[2][4];
     if (BONDS) {
@@ -352,10 +188,11 @@ update_color_kernel(const __grid_constant__ CUtensorMap src_tile, const __grid_c
         }
     }
 
-#if ISING_PROLOGUE == 2
     // No CTA-wide barrier: warp 0 initialises the mbarrier and then *arrives* on one named barrier
     // per other warp (ids 1..7, 64 threads each); warp w *syncs* on barrier w only just before it
     // first touches the mbarrier, ~1000 instructions later, when warp 0 has long since arrived.
+    // (A __syncthreads here held 11 % of all warp-stall samples: every warp waited for warp 0's
+    // mbarrier fence, which waited for warp 0's global loads.)
     if (threadIdx.x < 32) {
         if (threadIdx.x == 0) {
             mbar_init(&bar, 1);
@@ -366,17 +203,8 @@ update_color_kernel(const __grid_constant__ CUtensorMap src_tile, const __grid_c
 #pragma unroll
         for (int w = 1; w < UPDATE_THREADS / 32; w++) asm volatile("barrier.cta.arrive %0, 64;" ::"r"(w) : "memory");
     }
-#else
-    if (threadIdx.x == 0) {
-        mbar_init(&bar, 1);
-        fence_mbar_init();
-    }
-    __syncthreads();
-#endif
-#if ISING_PROLOGUE != 0
-    me[0] = my[0];     // issued after the mbarrier fence: a fence ahead of them would wait for these loads
+    me[0] = my[0];     // issued after the mbarrier fence: a fence behind them would wait for these loads
     me[1] = my[16];
-#endif
     if (threadIdx.x == 0) {
         if (PUSH) {   // ghost rows of the source colour must have arrived from the neighbours
             if (y0 == 0) while ((int)(ld_acquire_sys(p.wait_top) - p.wait_value) < 0) { }
@@ -411,16 +239,14 @@ update_color_kernel(const __grid_constant__ CUtensorMap src_tile, const __grid_c
 
     uint32_t rejA[2], rejB[2];
     if (FAST || p.rule.selB[0] | p.rule.selB[1] | p.rule.selB[2] | p.rule.selB[3] | p.rule.selB[4]) {
-        word_reject_masks<2, 0>(tc, p.st, p.rule.thrA, p.rule.thrB, p.zero, rejA[0], rejB[0]);
-        word_reject_masks<2, 1>(tc, p.st, p.rule.thrA, p.rule.thrB, p.zero, rejA[1], rejB[1]);
+        word_reject_masks<2, 0>(tc, p.st, p.rule.thrA, p.rule.thrB, rejA[0], rejB[0]);
+        word_reject_masks<2, 1>(tc, p.st, p.rule.thrA, p.rule.thrB, rejA[1], rejB[1]);
     } else {
-        word_reject_masks<1, 0>(tc, p.st, p.rule.thrA, p.rule.thrB, p.zero, rejA[0], rejB[0]);
-        word_reject_masks<1, 1>(tc, p.st, p.rule.thrA, p.rule.thrB, p.zero, rejA[1], rejB[1]);
+        word_reject_masks<1, 0>(tc, p.st, p.rule.thrA, p.rule.thrB, rejA[0], rejB[0]);
+        word_reject_masks<1, 1>(tc, p.st, p.rule.thrA, p.rule.thrB, rejA[1], rejB[1]);
     }
 
-#if ISING_PROLOGUE == 2
     if (threadIdx.x >= 32) asm volatile("barrier.cta.sync %0, 64;" ::"r"((int)(threadIdx.x >> 5)) : "memory");
-#endif
     mbar_wait(&bar, 0);
 
 #pragma unroll
@@ -524,8 +350,8 @@ __global__ void __launch_bounds__(UPDATE_THREADS) init_kernel(uint32_t* __restri
     const uint32_t tid = ref_tid(grow, (uint32_t)(x0 + tx), p.grid_x);
     const ThreadConsts tc = make_thread_consts(tid, p.st.x1, p.st.k1r3);
     uint32_t rej0, rej1, unused;
-    word_reject_masks<1, 0>(tc, p.st, p.thr_half, 0u, p.zero, rej0, unused);
-    word_reject_masks<1, 1>(tc, p.st, p.thr_half, 0u, p.zero, rej1, unused);
+    word_reject_masks<1, 0>(tc, p.st, p.thr_half, 0u, rej0, unused);
+    word_reject_masks<1, 1>(tc, p.st, p.thr_half, 0u, rej1, unused);
     uint32_t* r = plane + (size_t)row * p.pitch + x0 + tx;
     r[0] = ~rej0;
     r[16] = ~rej1;

@@ -39,7 +39,6 @@ struct UpdateParams {
     int yperiod;            // vertical wrap period in rows inside the slab; 0 = ghost rows
     int xperiod;            // horizontal wrap period in words
     int color;
-    uint32_t zero;          // always 0; a value ptxas cannot see through (see word_reject_masks)
     int bond_rows;          // rows of one bond plane as passed to the kernel (Y or Y+2)
     // Fused halo push (multi-slab, peer-mapped neighbours): the CTAs owning the slab's first / last
     // row store the new row into the neighbour's ghost row as well and count themselves done on the
@@ -62,7 +61,6 @@ struct InitParams {
     uint32_t grow0;
     int rows;
     int pitch;              // words per row
-    uint32_t zero;
 };
 
 struct BondParams {
