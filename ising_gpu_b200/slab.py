@@ -19,6 +19,31 @@ import torch.distributed as dist
 from .engine import F_NO_PEER_COPY, PART_ALL, PART_EDGES, PART_INTERIOR, IsingEngine
 
 
+def bind_process_near_gpu(device):
+    """Pin this process (and the pinned host memory it allocates from now on) to the NUMA node the GPU hangs
+    off: with one process per GPU and no binding, the staging buffers of half the ranks end up on the other
+    socket and every H2D/D2H crosses the inter-socket link.  Returns the node, or None when it cannot be
+    determined (no sysfs entry, a single node, no permission) -- then nothing is changed."""
+    import os
+    try:
+        pr = torch.cuda.get_device_properties(device)
+        bdf = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        node = int(open("/sys/bus/pci/devices/%s/numa_node" % bdf).read().strip())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return node
+    except Exception:
+        return None
+
+
 class HaloExchange:
     def __init__(self, rank, world, group=None):
         self.rank, self.world, self.group = rank, world, group
