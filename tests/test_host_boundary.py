@@ -79,3 +79,15 @@ def test_compute_calls_fail_loudly_without_gpu(ig):
         pytest.skip("GPU present")
     with pytest.raises(ig.IsingError):
         ig.IsingEngine(2048, 16)
+
+
+def test_numa_binding_is_a_no_op_without_a_gpu():
+    """slab.bind_process_near_gpu must never raise: without a GPU / sysfs entry it changes nothing."""
+    import os
+    import torch
+    from ising_gpu_b200.slab import bind_process_near_gpu
+    if torch.cuda.is_available():
+        pytest.skip("CPU-only check")
+    before = os.sched_getaffinity(0)
+    assert bind_process_near_gpu(0) is None
+    assert os.sched_getaffinity(0) == before
