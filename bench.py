@@ -12,16 +12,28 @@ its halo exchange).  The timed region holds exactly K steps, bracketed by a barr
 device synchronize, timed with CUDA events on the launching stream, max over ranks.
 
 One JSON line on rank 0.  `value` = total flip attempts of all ranks / that time, lattice
-resident in HBM.  `e2e` = same metric through the C ABI with HOST buffers: every step uploads
-both colour planes from pinned memory, sweeps, downloads the planes and the spin counts.
+resident in HBM.  `e2e` = same metric through the C ABI with HOST buffers, three ways: `value` =
+replica batch (every step uploads both colour planes from pinned memory, sweeps, downloads the
+step's observable), `with_lattice_download` = the same with the final planes downloaded too,
+`dependent_chain` = step k+1 starts from the planes step k downloaded (nothing can overlap).
 `roofline` = algorithmic bytes (0.25 B per flip attempt) over the measured kernel
-time against the measured HBM peak; `cpu_baseline` = numpy restatement of basic_python timed
-on this box's host (1 core), plus the C/OpenMP oracle on all cores as `cpu_oracle`.
+time against the measured HBM peak; `cpu_baseline` = numpy restatement of basic_python on
+BASELINE config 1 (256 x 256, T = 2.5, 128 sweeps; 1 core), `cpu_baseline_large` the same code at
+4096 x 4096, `cpu_oracle` the C/OpenMP oracle on all cores.
+
+Before the timed region both arms start from a fresh lattice and run steps x sweeps-per-step
+sweeps; the spin counts at that point are printed as `counts_at_sweeps` -- equal numbers in the
+two arms' lines prove bit-equality of the whole lattice history on the driver's own box (the counts
+at sweeps 16..128 are also asserted against the README transcripts where the lattice is one of
+theirs: `kat`).  `variants.tensorcore` = BASELINE config 4 (32768 x 32768 tensor-core variant,
+updates/ns) measured the same way in both arms.  At N > 1 `selfcheck` compares a small slab
+lattice run by all ranks with the 1-GPU engine before anything is timed.
 
 --impl reference: runs the UNMODIFIED reference (optimized/main.cu rebuilt for sm_100a as
-oracle/_ref/cuIsing_ref) through its own CLI on the same lattice; under torchrun only rank 0
-runs it (cuIsing_ref -d N drives all N GPUs from one process, as the reference does).  If the
-binary is absent it times the CPU oracle port on all host cores instead and says so.
+oracle/_ref/cuIsing_ref, tensorcore/main.cu as oracle/_ref/ising_tensorcore_ref) through its own
+CLI on the same lattice; under torchrun only rank 0 runs it (cuIsing_ref -d N drives all N GPUs
+from one process, as the reference does).  If the binary is absent it times the CPU oracle port on
+all host cores instead and says so.
 """
 import argparse
 import json
@@ -42,8 +54,32 @@ ALG_BYTES_PER_FLIP = 0.25      # each spin read once + written o
 REF_BYTES_PER_FLIP = 1.5       # the reference's own accounting, optimized/main.cu:1887-1890
 
 
+# tensor-core variant, BASELINE config 4 / SURVEY 8(d): 32768 x 32768 (-x 128 -y 128 in 256-blocks),
+# -a 0.661030 (T = 1.5), seed 1234; warm-up and trial iterations of the bench leg (reference CLI -w / -n)
+TC_NB, TC_ALPHA, TC_SEED, TC_WARM, TC_ITERS = 128, 0.661030, 1234, 20, 200
+TC_ALG_BYTES_PER_UPDATE = 2.0  # int8 lattice: every spin read once and written once per sweep
+
+# optimized/README.md:128-137 (65536 x 65536) and :240-249 (131072 x 65536): up-spin counts after n sweeps
+README_KAT = {
+    (1, 65536): ("optimized/README.md:128-137", {16: 2147575418, 32: 2147641872, 48: 2147605659, 64: 2147701147,
+                                                   80: 2147558546, 96: 2147471275, 112: 2147612509, 128: 2147678887}),
+    (2, 65536): ("optimized/README.md:240-249", {16: 4294617248, 32: 4293898346, 48: 4292806461, 64: 4291852263,
+                                                   80: 4291086016, 96: 4290256223, 112: 4289621029, 128: 4288877118}),
+}
+DEFAULT_SEED = 463463564571
+
+
 def default_rows(n):
     return 32768 if n >= 8 else 65536
+
+
+def workload_config(rows, n, seed, S):
+    """`config` of the JSON line: identical in both arms for the same command line."""
+    return {"workload": "checkerboard Metropolis, %dx%d lattice (%d rows per GPU), T=%.1f, seed %d, "
+                        "%d sweeps per step" % (rows * n, X_COLS, rows, TEMP, seed, S),
+            "l2_flush": "inputs larger than L2 (>= %d MiB of spins per GPU vs 126 MB L2)" % (rows * X_COLS // 8 >> 20),
+            "variants": "tensorcore: %dx%d tensor-core variant, alpha %.6f, seed %d, %d warm-up + %d trial iterations "
+                        "(1 GPU)" % (256 * TC_NB, 256 * TC_NB, TC_ALPHA, TC_SEED, TC_WARM, TC_ITERS)}
 
 
 class ClockSampler:
@@ -128,12 +164,21 @@ def ncu_pipe_summary():
 
 def cpu_baselines():
     from oracle import ising_oracle, numpy_basic
+    # BASELINE config 1: basic_python on 256 x 256, T = 2.5, 128 sweeps (repeated to fill ~10 s of CPU work)
+    reps, secs, fl, mag = 0, 0.0, [], 0.0
+    while secs < 10.0 and reps < 64:
+        f, mag, t = numpy_basic.run(n=256, m=256, alpha=2.5 / numpy_basic.TCRIT, sweeps=128, seed=1234 + reps)
+        fl.append(f); secs += t; reps += 1
+    base = {"value": round(sorted(fl)[len(fl) // 2], 5), "unit": "flips/ns", "cores": 1, "host_cores": os.cpu_count(),
+            "kind": "port", "abs_magnetisation_last_run": round(mag, 5),
+            "sample": "numpy restatement of basic_python/ising_basic.py update_lattice (pinned against the reference "
+                      "kernel under numba's simulator, tests/test_numpy_baseline.py), BASELINE config 1: 256x256, T=2.5, "
+                      "128 sweeps, median of %d runs, %.1f s" % (reps, secs)}
     n = 4096
-    sweeps = 24
+    sweeps = 12
     fl, mag, secs = numpy_basic.run(n=n, m=n, alpha=TEMP / numpy_basic.TCRIT, sweeps=sweeps, seed=1234)
-    base = {"value": round(fl, 5), "unit": "flips/ns", "cores": 1, "host_cores": os.cpu_count(), "kind": "port",
-            "sample": "numpy restatement of basic_python/ising_basic.py update_lattice, %dx%d, T=%.1f, %d sweeps, "
-                      "%.1f s" % (n, n, TEMP, sweeps, secs)}
+    large = {"value": round(fl, 5), "unit": "flips/ns", "cores": 1, "host_cores": os.cpu_count(), "kind": "port",
+             "sample": "same code, %dx%d, T=%.1f, %d sweeps, %.1f s" % (n, n, TEMP, sweeps, secs)}
     L = ising_oracle.OracleLattice(X_COLS, 4096)
     L.init()
     t0 = time.perf_counter()
@@ -142,7 +187,74 @@ def cpu_baselines():
     L.close()
     orc = {"value": round(X_COLS * 4096 * 2 / dt * 1e-9, 4), "unit": "flips/ns", "cores": ising_oracle.num_threads(),
            "kind": "port", "sample": "bit-exact C/OpenMP oracle of optimized/, 4096 rows x 65536, 2 sweeps, %.1f s" % dt}
-    return base, orc
+    return base, large, orc
+
+
+def tensorcore_leg(device):
+    """BASELINE config 4 through the C ABI (ising_tc_*): 32768 x 32768, warm-up + trial iterations numbered as the
+    reference numbers them; CUDA events on the launching stream inside ising_tc_update_timed."""
+    from ising_gpu_b200.tensorcore import TensorcoreEngine
+    peak, peak_src = measured_peaks()
+    traffic = None
+    try:
+        d = json.load(open(os.path.join(ROOT, "profiles", "tc_pipe_kernel_ncu_summary.json")))
+        traffic = float(d["dram_bytes_read"]) + float(d["dram_bytes_write"])
+    except Exception:
+        pass
+    sampler = ClockSampler(device)
+    with TensorcoreEngine(TC_NB, TC_NB, seed=TC_SEED, alpha=TC_ALPHA, device=device) as T:
+        T.init()
+        T.update(TC_WARM)
+        l0 = T.launches
+        ms = T.update_timed(TC_ITERS)
+        launches = T.launches - l0
+        n = float(T.nx) * T.ny
+        total = T.sum()
+    clocks = sampler.stop()
+    upd = n * TC_ITERS / (ms * 1e6)
+    kern_ms = ms / (2 * TC_ITERS)          # one colour update = one launch of the persistent kernel
+    alg = n / 2 * TC_ALG_BYTES_PER_UPDATE
+    ach = alg / (kern_ms * 1e-3) / 1e9
+    return {"metric": "updates/ns", "value": round(upd, 2), "unit": "updates/ns", "iterations": TC_ITERS,
+            "warmup_iterations": TC_WARM, "ms_per_iteration": round(ms / TC_ITERS, 4), "dtype": "int8 (tcgen05.mma kind::i8)",
+            "lattice": "%dx%d" % (T.nx, T.ny), "gpu_launches": int(launches),
+            "magnetism_after": {"iterations": TC_WARM + TC_ITERS, "value": "%g" % (abs(total) / n), "sum": total},
+            "roofline": {"bound": "hbm", "achieved": round(ach, 1), "peak": peak, "unit": "GB/s", "frac": round(ach / peak, 4),
+                         "traffic": traffic, "kernel": "tc_update_pipe_kernel", "kernel_ms": round(kern_ms, 4),
+                         "algorithmic_bytes_per_launch": alg, "peak_source": peak_src,
+                         "tensor_ops_per_update": 512},
+            "clocks": clocks}
+
+
+def selfcheck_slabs(a, rank, world, local):
+    """N > 1: a small lattice cut into `world` slabs and run by all ranks (same halo transport as the bench)
+    must equal the 1-GPU engine on the stacked lattice, bit for bit, after 3 sweeps."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from ising_gpu_b200.engine import IsingEngine
+    from ising_gpu_b200.slab import SlabEngine
+    X, Y, n = 4096, 64, 3
+    with torch.cuda.stream(torch.cuda.Stream()):
+        se = SlabEngine(X, Y, TEMP, a.seed, rank=rank, world=world, device=local, overlap=not a.no_overlap, halo=a.halo)
+    se.init_lattice()
+    se.sweeps(n)
+    torch.cuda.synchronize()
+    b, w = se.eng.export_bits()
+    allb = [None] * world
+    dist.all_gather_object(allb, (b, w))
+    se.close()
+    ok = True
+    if rank == 0:
+        with IsingEngine(X, Y * world, seed=a.seed, temp=TEMP, first_device=local) as one:
+            one.init_lattice()
+            one.sweeps(n)
+            ob, ow = one.export_bits()
+        ok = bool(np.array_equal(ob, np.vstack([x[0] for x in allb])) and np.array_equal(ow, np.vstack([x[1] for x in allb])))
+    t = torch.tensor([float(ok)], device="cuda", dtype=torch.float64)
+    dist.broadcast(t, 0)
+    return {"ok": bool(t.item()), "lattice": "%dx%d in %d slabs of %d rows, halo=%s" % (Y * world, X, world, Y, a.halo),
+            "sweeps": n, "against": "1-GPU engine on the stacked lattice, all spins compared"}
 
 
 def run_b200(a):
@@ -164,8 +276,6 @@ def run_b200(a):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     rows = a.rows_per_gpu or default_rows(world)
     S = a.sweeps_per_step
-    eng = SlabEngine(X_COLS, rows, TEMP, a.seed, rank=rank, world=world, device=local, overlap=not a.no_overlap,
-                     halo=a.halo)
 
     def barrier():
         torch.cuda.synchronize()
@@ -173,7 +283,41 @@ def run_b200(a):
             dist.barrier()
             torch.cuda.synchronize()
 
+    selfcheck = selfcheck_slabs(a, rank, world, local) if world > 1 and not a.no_selfcheck else None
+    if selfcheck is not None and not selfcheck["ok"]:
+        raise SystemExit("selfcheck failed: the slab decomposition does not reproduce the 1-GPU lattice: %r" % (selfcheck,))
+
+    eng = SlabEngine(X_COLS, rows, TEMP, a.seed, rank=rank, world=world, device=local, overlap=not a.no_overlap,
+                     halo=a.halo)
+
+    def total_counts():
+        up, dn = eng.count_spins()
+        if world > 1:
+            t = torch.tensor([up, dn], device="cuda", dtype=torch.int64)
+            dist.all_reduce(t)
+            up, dn = int(t[0]), int(t[1])
+        return up, dn
+
+    # ---- fresh lattice, steps x S sweeps: the counts both arms print (and, where the lattice is one of the
+    # README's, every 16th sweep up to 128 against its transcript).  Doubles as extra warm-up.
     eng.init_lattice()
+    kat_src, kat_tab = README_KAT.get((world, rows), (None, {})) if (a.seed == DEFAULT_SEED and TEMP == 1.5) else (None, {})
+    kat_checked, kat_ok, done = [], True, 0
+    total = S * a.steps
+    while done < total:
+        nxt = min(total, (done // 16 + 1) * 16) if kat_tab and done < 128 else total
+        eng.sweeps(nxt - done)
+        done = nxt
+        if done in kat_tab:
+            up, _ = total_counts()
+            kat_checked.append(done)
+            kat_ok = kat_ok and (up == kat_tab[done])
+    cas_up, cas_dn = total_counts()
+    counts_at = {"sweeps": total, "up": cas_up, "down": cas_dn, "from": "fresh lattice (Philox init), it = 1.."}
+    kat = {"source": kat_src, "sweeps_checked": kat_checked, "ok": kat_ok} if kat_checked else None
+    if kat is not None and not kat_ok:
+        raise SystemExit("spin counts differ from the reference's README transcript (%s)" % kat_src)
+
     for _ in range(a.warmup):
         eng.sweeps(S)
     sampler = ClockSampler(local) if rank == 0 else None
@@ -192,7 +336,7 @@ def run_b200(a):
         t = torch.tensor([ms], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
-    up, dn = eng.count_spins()
+    up, dn = total_counts()
     flips_per_rank = float(X_COLS) * rows * S * a.steps
     value = flips_per_rank * world / (ms * 1e6)
 
@@ -202,14 +346,23 @@ def run_b200(a):
         pitch = X_COLS // 64
         plane_bytes = rows * pitch * 4
         ksteps = max(1, min(a.steps, a.e2e_steps)) if a.e2e_steps else a.steps
+        flips_e2e = float(X_COLS) * rows * S * ksteps * world
 
         def pinned():
             t = torch.empty((rows, pitch), dtype=torch.int32).pin_memory()
             return t, t.numpy().view(np.uint32)
+
+        def allmax(*vals):
+            if world == 1:
+                return list(vals)
+            t = torch.tensor(list(vals), device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return [float(x) for x in t.tolist()]
         b0, w0 = eng.eng.export_bits()
 
-        def plain_e2e(nb, nw):
-            """One step after the other, nothing overlapped (the transport-agnostic path; also the fallback)."""
+        def chain_e2e(nb, nw):
+            """Dependent chain: step k+1 starts from the planes step k downloaded -- what a caller whose state
+            lives in host memory between steps pays; nothing can overlap."""
             def e2e_step():
                 eng.eng.import_bits(nb, nw)          # H2D of both colour planes (pinned)
                 eng.refresh_ghosts()                  # ghost rows belong to the uploaded state
@@ -224,20 +377,27 @@ def run_b200(a):
             barrier()
             return time.perf_counter() - t0
 
-        if world == 1:
-            # replica batch: every step is one job of the batch = upload both planes of a lattice from
-            # pinned memory, S sweeps, spin counts, download both planes; jobs alternate between two
-            # contexts so the copies of one step overlap the kernels of the next (ising_run_batch_from_host)
-            from ising_gpu_b200.engine import IsingEngine
-            eng2 = IsingEngine(X_COLS, rows, seed=a.seed, temp=TEMP, first_device=local)
-            keep, ins, outs = [], [], []
+        keep, ins, outs = [], [], []
+        ready = True
+        try:        # pinned host memory is the one local resource that can run out here
             for j in range(2):
                 (tb, nb), (tw, nw) = pinned(), pinned()
                 nb[:], nw[:] = b0, w0
                 (tob, nob), (tow, now) = pinned(), pinned()
                 keep += [tb, tw, tob, tow]
                 ins.append((nb, nw)); outs.append((nob, now))
-            del b0, w0
+        except RuntimeError:
+            ready = False
+        ready = bool(-allmax(-float(ready))[0])           # every rank enters the batch, or none does
+        runs_dl, runs = [], []
+        ok = False
+        api = None
+        if ready and world == 1:
+            # replica batch: every step is one job of the batch = upload both planes of a lattice from
+            # pinned memory, S sweeps, spin counts, download both planes; jobs alternate between two
+            # contexts so the copies of one step overlap the kernels of the next (ising_run_batch_from_host)
+            from ising_gpu_b200.engine import IsingEngine
+            eng2 = IsingEngine(X_COLS, rows, seed=a.seed, temp=TEMP, first_device=local)
 
             def batch(k, download):
                 return eng.eng.run_batch_from_host(eng2, [ins[j & 1][0] for j in range(k)],
@@ -245,27 +405,10 @@ def run_b200(a):
                                                    [outs[j & 1][0] for j in range(k)] if download else None,
                                                    [outs[j & 1][1] for j in range(k)] if download else None,
                                                    first_it=eng.it + 1)
-
-            def timed(download):
-                batch(2, download)
-                best = None
-                for _ in range(2):                   # best of 2 runs of K steps (host-side transients)
-                    barrier()
-                    t0 = time.perf_counter()
-                    counts = batch(ksteps, download)
-                    barrier()
-                    d = time.perf_counter() - t0
-                    best = d if best is None else min(best, d)
-                return best, counts
-            dt_dl, counts = timed(True)              # D2H of the final planes as well (a checkpoint per step)
-            assert len(set(counts)) == 1 and counts[0][0] + counts[0][1] == X_COLS * rows, counts
-            assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1])
-            dt, counts2 = timed(False)               # D2H of the step's observable only
-            assert counts2 == counts
-            eng2.close()
+            want_counts = None
             api = ("ising_run_batch_from_host (C ABI, pinned host buffers): per step H2D of both planes, %d sweeps, "
                    "count kernels, D2H of the spin counts; two contexts, copies overlap the other step's kernels" % S)
-        elif a.halo == "fused":
+        elif ready and a.halo == "fused":
             # the same replica batch on every rank's slab (ising_run_slab_batch_from_host): per step H2D of the
             # slab's planes and white ghost rows, S sweeps with the fused halo push between the ranks, counts,
             # D2H of the planes; two contexts per rank so that copies overlap the other step's kernels
@@ -282,93 +425,77 @@ def run_b200(a):
             want_b, want_w = eng.eng.export_bits()
             want_counts = eng.count_spins()
             eng.it = eng2.it = it0
-            keep, ins, outs, ready = [], [], [], True
-            try:        # pinned host memory is the one local resource that can run out here
-                for j in range(2):
-                    (tb, nb), (tw, nw) = pinned(), pinned()
-                    nb[:], nw[:] = b0, w0
-                    (tob, nob), (tow, now) = pinned(), pinned()
-                    keep += [tb, tw, tob, tow]
-                    ins.append((nb, nw)); outs.append((nob, now))
-                tg = torch.empty((2, pitch), dtype=torch.int32).pin_memory()
-                ng = tg.numpy().view(np.uint32)
-                ng[:] = ghosts
-            except RuntimeError:
-                ready = False
-            t = torch.tensor([float(ready)], device="cuda", dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MIN)        # every rank enters the batch, or none does
-            ready = bool(t.item())
-            dt, ok = 1.0, False
-            if ready:
-                del b0, w0
+            tg = torch.empty((2, pitch), dtype=torch.int32).pin_memory()
+            ng = tg.numpy().view(np.uint32)
+            ng[:] = ghosts
 
-                def batch(k, download):
-                    return eng.run_batch_from_host(eng2, [ins[j & 1][0] for j in range(k)],
-                                                   [ins[j & 1][1] for j in range(k)], [ng] * k, S,
-                                                   [outs[j & 1][0] for j in range(k)] if download else None,
-                                                   [outs[j & 1][1] for j in range(k)] if download else None)
-
-                def timed(download):
-                    batch(2, download)
-                    best = None
-                    for _ in range(2):               # best of 2 runs of K steps (host-side transients); the ranks
-                        barrier()                    # agree on the maximum of their best times below
-                        t0 = time.perf_counter()
-                        counts = batch(ksteps, download)
-                        barrier()
-                        d = time.perf_counter() - t0
-                        best = d if best is None else min(best, d)
-                    return best, counts
-                dt_dl, counts = timed(True)          # D2H of the final planes as well (a checkpoint per step)
-                ok = all(c == want_counts for c in counts) and all(
-                    np.array_equal(ob, want_b) and np.array_equal(ow, want_w) for ob, ow in outs[:min(2, ksteps)])
-                dt, counts2 = timed(False)           # D2H of the step's observable only
-                ok = ok and counts2 == counts
-            del want_b, want_w
-            t = torch.tensor([dt, -float(ok), dt_dl if ready else 1.0], device="cuda", dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            dt, ok, dt_dl = float(t[0].item()), float(t[1].item()) == -1.0, float(t[2].item())   # ok on every rank
-            eng2.close()
+            def batch(k, download):
+                return eng.run_batch_from_host(eng2, [ins[j & 1][0] for j in range(k)],
+                                               [ins[j & 1][1] for j in range(k)], [ng] * k, S,
+                                               [outs[j & 1][0] for j in range(k)] if download else None,
+                                               [outs[j & 1][1] for j in range(k)] if download else None)
             api = ("ising_run_slab_batch_from_host (C ABI, pinned host buffers): per step and rank H2D of the slab's planes "
                    "and white ghost rows, %d sweeps with the fused halo push, count kernels, D2H of the spin counts; "
                    "two contexts per rank, copies overlap the other step's kernels; result checked against the "
                    "unpipelined path" % S)
-            if not ok:   # never report a number for a wrong result: measure the plain path instead and say so
-                dt_dl = None
-                if not ready:
-                    keep, ins = [], []
-                    (tb, nb), (tw, nw) = pinned(), pinned()
-                    nb[:], nw[:] = b0, w0
-                    ins.append((nb, nw))
-                dt = plain_e2e(ins[0][0], ins[0][1])
-                t = torch.tensor([dt], device="cuda", dtype=torch.float64)
-                dist.all_reduce(t, op=dist.ReduceOp.MAX)
-                dt = float(t.item())
-                api = (("PIPELINED RESULT MISMATCH" if ready else "pinned host memory exhausted") +
-                       ", fell back to ising_import_bits + ising_sweeps + ising_export_bits + "
-                       "ising_count_spins per step, not pipelined")
         else:
-            (hb, nb), (hw, nw) = pinned(), pinned()
-            nb[:], nw[:] = b0, w0
-            del b0, w0
-            dt = plain_e2e(nb, nw)
-            dt_dl = None
-            t = torch.tensor([dt], device="cuda", dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            dt = float(t.item())
-            api = ("ising_import_bits + ising_sweeps + ising_export_bits + ising_count_spins per step "
-                   "(C ABI, pinned host buffers), not pipelined")
-        pipelined = dt_dl is not None
-        h2d = (2 * plane_bytes + (2 * pitch * 4 if world > 1 and pipelined else 0)) * world
-        e2e = {"value": round(float(X_COLS) * rows * S * ksteps * world / (dt * 1e9), 2), "unit": "flips/ns",
-               "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": (8 if pipelined else 2 * plane_bytes + 8) * world,
-               "steps": ksteps, "timer": "host monotonic clock around the synchronised region" +
-               (", best of 2 runs of %d steps" % ksteps if pipelined else ""), "api": api,
-               "numa_node_of_rank0": numa}
-        if pipelined:   # the same batch with the final lattice of every step downloaded as well
-            e2e["with_lattice_download"] = {"value": round(float(X_COLS) * rows * S * ksteps * world / (dt_dl * 1e9), 2),
-                                            "unit": "flips/ns", "h2d_bytes_per_step": h2d,
-                                            "d2h_bytes_per_step": (2 * plane_bytes + 8) * world}
+            batch = None
+        if batch is not None:
+            def timed(download):
+                batch(2, download)
+                out = []
+                for _ in range(2):                   # two runs of K steps, both reported; the better one is the value
+                    barrier()                        # (the reference arm does the same)
+                    t0 = time.perf_counter()
+                    counts = batch(ksteps, download)
+                    barrier()
+                    out.append(time.perf_counter() - t0)
+                return out, counts
+            runs_dl, counts = timed(True)            # D2H of the final planes as well (a checkpoint per step)
+            if world == 1:
+                ok = (len(set(counts)) == 1 and counts[0][0] + counts[0][1] == X_COLS * rows and
+                      np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1]))
+            else:
+                ok = all(c == want_counts for c in counts) and all(
+                    np.array_equal(ob, want_b) and np.array_equal(ow, want_w) for ob, ow in outs[:min(2, ksteps)])
+            runs, counts2 = timed(False)             # D2H of the step's observable only
+            ok = ok and counts2 == counts
+            ok = bool(-allmax(-float(ok))[0])
+            runs_dl = [allmax(x)[0] for x in runs_dl]
+            runs = [allmax(x)[0] for x in runs]
+            eng2.close()
+            if not ok:
+                raise SystemExit("e2e: pipelined replica batch does not reproduce the unpipelined result")
+        # dependent chain on one of the input buffers (always measured; the only e2e number without a batch)
+        if ins:
+            ins[0][0][:], ins[0][1][:] = b0, w0
+            cb, cw = ins[0]
+        else:
+            (tb, cb), (tw, cw) = pinned(), pinned()
+            cb[:], cw[:] = b0, w0
+        del b0, w0
+        dt_chain = allmax(chain_e2e(cb, cw))[0]
+        chain = {"value": round(flips_e2e / (dt_chain * 1e9), 2), "unit": "flips/ns",
+                 "h2d_bytes_per_step": 2 * plane_bytes * world, "d2h_bytes_per_step": (2 * plane_bytes + 8) * world,
+                 "api": "ising_import_bits + ising_sweeps + ising_export_bits + ising_count_spins per step (C ABI, pinned "
+                        "host buffers): step k+1 uploads what step k downloaded, nothing overlaps"}
+        if batch is not None:
+            h2d = (2 * plane_bytes + (2 * pitch * 4 if world > 1 else 0)) * world
+            e2e = {"value": round(flips_e2e / (min(runs) * 1e9), 2), "unit": "flips/ns",
+                   "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 8 * world, "steps": ksteps,
+                   "timer": "host monotonic clock around the synchronised region, max over ranks; two runs of %d steps, "
+                            "the better one is `value`" % ksteps,
+                   "runs": [round(flips_e2e / (x * 1e9), 2) for x in runs], "api": api, "numa_node_of_rank0": numa,
+                   "with_lattice_download": {"value": round(flips_e2e / (min(runs_dl) * 1e9), 2), "unit": "flips/ns",
+                                             "runs": [round(flips_e2e / (x * 1e9), 2) for x in runs_dl],
+                                             "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": (2 * plane_bytes + 8) * world},
+                   "dependent_chain": chain}
+        else:
+            e2e = dict(chain)
+            e2e.update({"steps": ksteps, "timer": "host monotonic clock around the synchronised region, max over ranks",
+                        "numa_node_of_rank0": numa, "dependent_chain": chain,
+                        "note": "no replica batch on this transport (halo=%s%s)" % (a.halo, "" if ready else
+                                                                                   ", pinned host memory exhausted")})
 
     out = None
     if rank == 0:
@@ -388,30 +515,57 @@ def run_b200(a):
         out = {"metric": "spin-flip attempts/ns", "value": round(value, 2), "unit": "flips/ns", "n_gpus": world,
                "steps": a.steps, "warmup": a.warmup, "ms_per_step": round(ms / a.steps, 4), "higher_is_better": True,
                "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
-               "config": {"workload": "checkerboard Metropolis, %dx%d lattice (%d rows per GPU), T=%.1f, seed %d, "
-                                      "%d sweeps per step" % (rows * world, X_COLS, rows, TEMP, a.seed, S),
-                          "lattice_bytes_per_gpu": rows * X_COLS // 8, "l2_flush": "inputs larger than L2 "
-                          "(%d MiB of spins per GPU vs 126 MB L2)" % (rows * X_COLS // 8 >> 20),
-                          "halo": "none" if world == 1 else (
-                              "fused: update kernel stores its edge rows into the neighbours' ghost rows (CUDA IPC "
-                              "peer memory over NVLink) and signals device-side counters" if a.halo == "fused" else
-                              "NCCL send/recv of 1 row per direction per colour, " +
-                              ("overlapped with the interior update" if not a.no_overlap else "serialised"))},
+               "config": workload_config(rows, world, a.seed, S),
+               "details": {"lattice_bytes_per_gpu": rows * X_COLS // 8,
+                           "halo": "none" if world == 1 else (
+                               "fused: update kernel stores its edge rows into the neighbours' ghost rows (CUDA IPC "
+                               "peer memory over NVLink) and signals device-side counters" if a.halo == "fused" else
+                               "NCCL send/recv of 1 row per direction per colour, " +
+                               ("overlapped with the interior update" if not a.no_overlap else "serialised")),
+                           "update_kernel": os.environ.get("ISING_B200_KERNEL", "default")},
                "roofline": roof, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
-               "final_counts": {"up": up if world == 1 else None, "down": dn if world == 1 else None}}
-        if world == 1 and not a.no_cpu:
-            out["cpu_baseline"], out["cpu_oracle"] = cpu_baselines()
+               "counts_at_sweeps": counts_at, "kat": kat, "selfcheck": selfcheck,
+               "final_counts": {"up": up, "down": dn, "sweeps": total + S * (a.warmup + a.steps)}}
     if world > 1:
-        # total spin counts as a cross-rank checksum
-        t = torch.tensor([up, dn], device="cuda", dtype=torch.int64)
-        dist.all_reduce(t)
-        if rank == 0:
-            out["final_counts"] = {"up": int(t[0]), "down": int(t[1])}
         dist.barrier()
-        dist.destroy_process_group()
     eng.close()
     if rank == 0:
+        variants = {}
+        if world == 1 and not a.no_tc:
+            variants["tensorcore"] = tensorcore_leg(local)
+        out["variants"] = variants
+        if world == 1 and not a.no_cpu:
+            out["cpu_baseline"], out["cpu_baseline_large"], out["cpu_oracle"] = cpu_baselines()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank == 0:
         _GUARD.emit(json.dumps(out))
+
+
+def reference_tensorcore_leg():
+    """The reference's tensorcore/ program (oracle/_ref/ising_tensorcore_ref, stock CLI) on BASELINE config 4;
+    "updates per ns" and "average magnetism" parsed from its REPORT block (tensorcore/main.cu:601-609, :638)."""
+    binary = os.path.join(ROOT, "oracle", "_ref", "ising_tensorcore_ref")
+    if not os.access(binary, os.X_OK):
+        return {"unavailable": "oracle/_ref/ising_tensorcore_ref not built"}
+    cmd = [binary, "-x", str(TC_NB), "-y", str(TC_NB), "-w", str(TC_WARM), "-n", str(TC_ITERS), "-a", "%.6f" % TC_ALPHA,
+           "-s", str(TC_SEED)]
+    try:
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+    except subprocess.TimeoutExpired:
+        return {"unavailable": "reference tensorcore run timed out"}
+    m = re.search(r"updates per ns:\s*(\S+)", r.stdout)
+    if not m:
+        return {"unavailable": "reference tensorcore run failed: " + (r.stderr or r.stdout)[-300:]}
+    el = re.search(r"elapsed time:\s*(\S+) sec", r.stdout)
+    mg = re.search(r"average magnetism \(absolute\):\s*(\S+)", r.stdout)
+    return {"metric": "updates/ns", "value": float(m.group(1)), "unit": "updates/ns", "iterations": TC_ITERS,
+            "warmup_iterations": TC_WARM, "ms_per_iteration": round(float(el.group(1)) * 1e3 / TC_ITERS, 4) if el else None,
+            "dtype": "fp16 (cuBLAS batched HGEMM, tensor op)", "lattice": "%dx%d" % (256 * TC_NB, 256 * TC_NB),
+            "magnetism_after": {"iterations": TC_WARM + TC_ITERS, "value": mg.group(1) if mg else None},
+            "reference_kind": "tensorcore/main.cu for sm_100a, only its final CUB reduce replaced "
+                              "(oracle/build_ref_tensorcore.py), run through its own CLI: " + " ".join(cmd[1:])}
 
 
 def run_reference(a):
@@ -425,8 +579,7 @@ def run_reference(a):
     binary = os.path.join(ROOT, "oracle", "_ref", "cuIsing_ref")
     base = {"metric": "spin-flip attempts/ns", "unit": "flips/ns", "n_gpus": n, "steps": a.steps, "warmup": a.warmup,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "data": "synthetic", "impl": "reference",
-            "config": {"workload": "checkerboard Metropolis, %dx%d lattice (%d rows per GPU), T=%.1f, seed %d, "
-                                   "%d sweeps per step" % (rows * n, X_COLS, rows, TEMP, a.seed, S)}}
+            "config": workload_config(rows, n, a.seed, S)}
     try:
         have_gpu = subprocess.run(["nvidia-smi", "-L"], capture_output=True).returncode == 0
     except OSError:
@@ -444,16 +597,25 @@ def run_reference(a):
             return float(m.group(2)), float(m.group(3)), (int(fin.group(1)), int(fin.group(2))) if fin else None
         try:
             if a.warmup:
-                call(max(1, a.warmup))
-            ms, fl, fin = call(S * a.steps)
+                call(S * a.warmup)      # same number of warm-up sweeps as the other arm (separate process: the
+                                        # reference CLI has no warm-up option; clocks and driver state are warm)
+            runs = [call(S * a.steps) for _ in range(2)]    # two runs, both reported, the better one is the value
+            ms, fl, fin = max(runs, key=lambda r: r[1])
             base.update({"value": fl, "ms_per_step": round(ms / a.steps, 4), "dtype": "u64 (4 bit/spin)",
+                         "runs": [r[1] for r in runs],
                          "reference_kind": "unmodified optimized/main.cu + utils.c, nvcc -O3 --use_fast_math for "
-                                           "sm_100a, run through its own CLI (cuIsing_ref -d %d)" % n,
-                         "final_counts": {"up": fin[0], "down": fin[1]} if fin else None,
+                                           "sm_100a, run through its own CLI (cuIsing_ref -d %d), lattice resident "
+                                           "on the GPU(s)" % n,
+                         "counts_at_sweeps": {"sweeps": S * a.steps, "up": fin[0], "down": fin[1],
+                                              "from": "fresh lattice (its own init), its Final magnetization line"} if fin else None,
+                         "final_counts": {"up": fin[0], "down": fin[1], "sweeps": S * a.steps} if fin else None,
                          "cpu_baseline": {"value": fl, "unit": "flips/ns", "cores": 0, "kind": "reference",
                                           "sample": "GPU reference binary, not a CPU run: %d sweeps of the full "
                                                     "workload" % (S * a.steps)},
-                         "e2e": {"value": fl, "unit": "flips/ns", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
+                         "e2e": {"value": fl, "unit": "flips/ns", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+                                 "note": "resident only: the reference CLI has no host-buffer entry point, its lattice "
+                                         "never leaves the GPU"}})
+            base["variants"] = {"tensorcore": reference_tensorcore_leg()} if (n == 1 and not a.no_tc) else {}
             _GUARD.emit(json.dumps(base))
             return
         except Exception as e:   # fall through to the CPU port
@@ -504,6 +666,8 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=0, help="steps of the e2e leg (0 = --steps)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-tc", action="store_true", help="skip the tensor-core variant leg (variants.tensorcore)")
+    ap.add_argument("--no-selfcheck", action="store_true", help="N > 1: skip the small slab-vs-1-GPU comparison")
     ap.add_argument("--no-overlap", action="store_true")
     ap.add_argument("--halo", default="fused", choices=["fused", "nccl"],
                     help="fused: the update kernel stores boundary rows into the neighbours' ghost rows over NVLink "

@@ -35,6 +35,8 @@ extern "C" {
 #define ISING_B200_ABI_VERSION 1
 
 #define ISING_MAX_DEVICES 256          /* MAX_GPU, optimized/main.cu:60 */
+#define ISING_MAX_CORR_DEVICES 16      /* ising_correlation: devices of one context                     */
+#define ISING_MAX_CORR_ROW_BYTES 204800 /* ising_correlation: X / 8 (one lattice row at 1 bit/spin) limit  */
 #define ISING_DEFAULT_SEED 463463564571ull /* SEED_DEF, optimized/main.cu:63 */
 #define ISING_CRIT_TEMP 2.26918531421f /* CRIT_TEMP, optimized/main.cu:42 */
 
@@ -44,7 +46,8 @@ enum {
     ISING_ECUDA = -2,   /* a CUDA runtime/driver call failed (CHECK_CUDA, cudamacro.h:25)    */
     ISING_ENOPEER = -3, /* missing direct link between devices (main.cu:1531-1536)           */
     ISING_ENOMEM = -4,
-    ISING_ESTATE = -5   /* call not valid in this state (e.g. halo access on a 1-slab ctx)   */
+    ISING_ESTATE = -5,  /* call not valid in this state (e.g. halo access on a 1-slab ctx)   */
+    ISING_ETIMEOUT = -6 /* a device-side wait for a neighbouring slab's halo rows gave up    */
 };
 
 enum { ISING_BLACK = 0, ISING_WHITE = 1 }; /* enum {C_BLACK, C_WHITE}, main.cu:80 */
@@ -113,6 +116,8 @@ int ising_sweeps_timed(ising_ctx* ctx, int first_it, int n, float* ms);
 
 /* Rebuild the acceptance table for a new temperature (main.cu:1848-1859). */
 int ising_set_temperature(ising_ctx* ctx, float temp);
+/* temperature currently in force (after ising_set_temperature or ising_load_checkpoint) */
+int ising_get_temperature(const ising_ctx* ctx, float* temp);
 
 /* ---- observables -----------------------------------------------------------------------*/
 /* countSpins / getMagn_k (main.cu:831-868): #up and #down over the context's slabs. */
@@ -125,7 +130,10 @@ int ising_bond_sum(ising_ctx* ctx, int64_t* bond_sum);
  * out[j-1], j = 1..ncorr (the reference uses 128), = sum over all sites of (+1 if equal else -1)
  * for the site j columns to the right and the site j rows below, periodic inside the
  * (sub-)lattice, divided by 2*X*rows -- the numbers the reference writes to its corr_ file.
- * Single-process contexts only (any ndev). */
+ * Single-process contexts only, up to ISING_MAX_CORR_DEVICES devices and X / 8 <= ISING_MAX_CORR_ROW_BYTES
+ * (ISING_ESTATE otherwise; the CLI checks both when it parses -c).  For X (or xsl) not a multiple of 4096 the
+ * reference's chunk loop (main.cu:905) counts columns twice and reads past the row; this returns the exact
+ * periodic two-point function instead (the CLI prints a warning). */
 int ising_correlation(ising_ctx* ctx, int ncorr, double* out);
 /* +-J bond nibbles of one device's slab in the reference's 4-bit words (bit 3 up, 2 down, 1 left,
  * 0 right): `random` = the buffer hamiltInitB_k fills (used by the WHITE update, main.cu:1796),
@@ -141,10 +149,11 @@ int ising_import_ref_layout(ising_ctx* ctx, int dev, const uint64_t* black, cons
 int ising_export_bits(ising_ctx* ctx, int dev, uint32_t* black, uint32_t* white);
 int ising_import_bits(ising_ctx* ctx, int dev, const uint32_t* black, const uint32_t* white);
 /* Binary checkpoint of every device of the context (the reference has none): a header
- * (shape, slabs, seed, temperature, sweeps done) and the bit-packed colour planes.  Loading checks the
- * shape and the seed -- the continuation draws from the same Philox stream, so `n1` sweeps, save,
- * load, `n2` sweeps starting at iteration n1 + 1 equal n1 + n2 sweeps -- and refreshes the ghost rows
- * between the context's own devices.  iterations_done may be NULL. */
+ * (shape, slabs, seed, temperature, -J flag and probability, sweeps done) and the bit-packed colour planes.
+ * Loading checks the shape, the seed and the Hamiltonian (-J), restores the saved temperature
+ * (ising_get_temperature tells the caller) -- the continuation draws from the same Philox stream, so `n1`
+ * sweeps, save, load, `n2` sweeps starting at iteration n1 + 1 equal n1 + n2 sweeps -- and refreshes the
+ * ghost rows between the context's own devices.  iterations_done may be NULL. */
 int ising_save_checkpoint(ising_ctx* ctx, const char* path, uint64_t iterations_done);
 int ising_load_checkpoint(ising_ctx* ctx, const char* path, uint64_t* iterations_done);
 /* dumpLattice (main.cu:1140-1209): writes "<prefix><dev>.txt" for every device of the context. */
@@ -186,7 +195,10 @@ int ising_run_slab_batch_from_host(ising_ctx* ctx_a, ising_ctx* ctx_b, int nrep,
  * fills ghost rows (from the neighbouring slabs' rows Y-1 / 0) between colour updates. */
 int ising_row_ptr(ising_ctx* ctx, int dev, int color, int row, void** dptr, size_t* nbytes);
 /* Update only the tile rows that touch the slab edge (first/last 16 rows) or only the rest;
- * lets the caller overlap the halo exchange with the interior (see engine.SlabEngine). */
+ * lets the caller overlap the halo exchange with the interior (see engine.SlabEngine).
+ * Only for contexts whose ghost rows the CALLER fills (ISING_F_NO_PEER_COPY, no ising_ipc_attach):
+ * on a context with the fused halo push it returns ISING_ESTATE (the push of a partial launch
+ * would not be counted and the ghost-row ordering would be lost). */
 enum { ISING_PART_ALL = 0, ISING_PART_EDGES = 1, ISING_PART_INTERIOR = 2 };
 int ising_update_color_part(ising_ctx* ctx, int dev, int color, int it, int part, void* stream);
 

@@ -72,6 +72,7 @@ struct DevState {
     unsigned int* up_flags = nullptr;
     unsigned int* dn_flags = nullptr;
     void* ipc_opened[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    int sms = 148;                             // multiprocessors: the persistent update kernel runs sms x 4 CTAs
     cudaEvent_t ev_color = nullptr;            // kernel + halo pushes of the last colour issued
     cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;
 };
@@ -84,6 +85,9 @@ struct ising_ctx {
     int slab_count = 1;
     bool bonds = false;
     bool fused = false;       // halo rows are pushed by the update kernel itself (peer stores + counters)
+    bool persistent = false;  // ISING_B200_KERNEL=persistent selects the persistent kernel (A/B; measured 3 % slower)
+    bool split_edges = true;  // tile kernel, fused push: edge tile rows in their own launch ahead of the interior
+    unsigned long long spin_timeout_ns = 30ull * 1000000000ull;   // bound of every device-side wait on a neighbour
     uint64_t pushes_done[2] = {0, 0};
     bool peer_halo = false;   // library copies boundary rows between its own devices
     bool ghost_rows = false;  // vertical neighbours of the slab edge come from ghost rows
@@ -95,6 +99,9 @@ struct ising_ctx {
 };
 
 namespace {
+
+constexpr int FLAG_WORDS = 16;      // d_flags: [0..3] arrival counters, [ERR_FLAG_WORD] error word
+constexpr int ERR_FLAG_WORD = 8;
 
 uint32_t* local_row(const ising_ctx* c, const DevState& d, int color, int row)
 {
@@ -166,6 +173,15 @@ int launch_part(ising_ctx* c, int dev, int color, int it, int part, cudaStream_t
         if (gy <= 0) return ISING_OK;
     }
     p.launch_tile_rows = gy;
+    p.err_flag = d.d_flags ? d.d_flags + ERR_FLAG_WORD : nullptr;
+    p.spin_timeout_ns = c->spin_timeout_ns;
+    if (c->persistent) {
+        // edge tile rows are the first tiles of the walk whenever the launch owns them: the fused halo
+        // push leaves in the first iteration of the same launch that does the interior
+        p.edges_mode = 0;
+        p.edges_first = (part == ISING_PART_EDGES) || (part == ISING_PART_ALL && c->fused);
+        if (p.edges_first) { p.tile_row0 = 0; p.tile_row_alt = tiles_y - 1; }
+    }
     if (c->fused && part != ISING_PART_INTERIOR) {   // the launch that owns the edge rows pushes them
         const int Y = c->cfg.Y;
         p.push = 1;
@@ -182,8 +198,12 @@ int launch_part(ising_ctx* c, int dev, int color, int it, int part, cudaStream_t
     // hamiltInitB_k one (main.cu:1775, :1796)
     const uint32_t* bonds = nullptr;
     if (c->bonds) bonds = (color == 0) ? d.bond_mirror : d.bond_random + c->pitch;   // local row 0
-    launch_update(d.map_tile[src], d.map_row[src], d.map_side[src], local_row(c, d, color, 0), bonds, p, tiles_x, gy,
-                  stream);
+    if (c->persistent)
+        launch_update_persistent(d.map_tile[src], d.map_row[src], d.map_side[src], d.map_tile[color],
+                                 local_row(c, d, color, 0), bonds, p, tiles_x, gy, d.sms, stream);
+    else
+        launch_update(d.map_tile[src], d.map_row[src], d.map_side[src], local_row(c, d, color, 0), bonds, p, tiles_x, gy,
+                      stream);
     CU_TRY(cudaGetLastError());
     c->launches++;
     return ISING_OK;
@@ -296,6 +316,12 @@ int ising_create(const ising_cfg* cfg, ising_ctx** out)
     c->rule = make_rule(cfg->temp);
     c->thr_half = (uint32_t)(accept_count(0.5f, true) - 1);
     c->dev.resize(cfg->ndev);
+    if (const char* k = getenv("ISING_B200_KERNEL")) c->persistent = strcmp(k, "persistent") == 0;
+    if (const char* k = getenv("ISING_B200_SPLIT_EDGES")) c->split_edges = atoi(k) != 0;
+    if (const char* t = getenv("ISING_B200_SPIN_TIMEOUT_MS")) {
+        const long long ms = atoll(t);
+        if (ms > 0) c->spin_timeout_ns = (unsigned long long)ms * 1000000ull;
+    }
 
     auto cleanup = [&](int rc) { ising_destroy(c); return rc; };
     for (int i = 0; i < cfg->ndev; i++) c->dev[i].device = cfg->first_device + i;
@@ -324,6 +350,7 @@ int ising_create(const ising_cfg* cfg, ising_ctx** out)
         if ((e = cudaSetDevice(d.device)) != cudaSuccess) return cleanup(fail(ISING_ECUDA, "cudaSetDevice(%d): %s", d.device, cudaGetErrorString(e)));
         cudaDeviceProp prop;
         if ((e = cudaGetDeviceProperties(&prop, d.device)) != cudaSuccess) return cleanup(fail(ISING_ECUDA, "%s", cudaGetErrorString(e)));
+        d.sms = prop.multiProcessorCount;
         if (prop.major < 10) return cleanup(fail(ISING_ECUDA, "device %d is sm_%d%d; this library is built for sm_100a only", d.device, prop.major, prop.minor));
         if ((e = cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking)) != cudaSuccess) return cleanup(fail(ISING_ECUDA, "stream: %s", cudaGetErrorString(e)));
         for (int col = 0; col < 2; col++) {
@@ -336,8 +363,8 @@ int ising_create(const ising_cfg* cfg, ising_ctx** out)
         }
         if ((e = cudaMalloc(&d.d_counts, 2 * sizeof(unsigned long long))) != cudaSuccess) return cleanup(fail(ISING_ENOMEM, "%s", cudaGetErrorString(e)));
         if (c->ghost_rows) {
-            if ((e = cudaMalloc(&d.d_flags, 8 * sizeof(unsigned int))) != cudaSuccess ||
-                (e = cudaMemsetAsync(d.d_flags, 0, 8 * sizeof(unsigned int), d.stream)) != cudaSuccess)
+            if ((e = cudaMalloc(&d.d_flags, FLAG_WORDS * sizeof(unsigned int))) != cudaSuccess ||
+                (e = cudaMemsetAsync(d.d_flags, 0, FLAG_WORDS * sizeof(unsigned int), d.stream)) != cudaSuccess)
                 return cleanup(fail(ISING_ENOMEM, "flags: %s", cudaGetErrorString(e)));
         }
         if (c->bonds) {
@@ -408,6 +435,13 @@ int ising_set_temperature(ising_ctx* c, float temp)
     return ISING_OK;
 }
 
+int ising_get_temperature(const ising_ctx* c, float* temp)
+{
+    if (!c || !temp) return fail(ISING_EINVAL, "bad argument");
+    *temp = c->cfg.temp;
+    return ISING_OK;
+}
+
 int ising_init_lattice(ising_ctx* c)
 {
     if (!c) return fail(ISING_EINVAL, "null context");
@@ -457,8 +491,9 @@ int ising_correlation(ising_ctx* c, int ncorr, double* out)
     if (!c || !out || ncorr < 1 || ncorr > 4096) return fail(ISING_EINVAL, "bad argument");
     const int n = (int)c->dev.size();
     if (c->slab_count != n) return fail(ISING_ESTATE, "ising_correlation needs the whole lattice in one context");
+    static_assert(MAX_CORR_SLABS == ISING_MAX_CORR_DEVICES, "header limit out of sync");
     if (n > MAX_CORR_SLABS) return fail(ISING_ESTATE, "ising_correlation supports up to %d devices", MAX_CORR_SLABS);
-    if (2 * (size_t)c->pitch * 4 > 200 * 1024) return fail(ISING_ESTATE, "X too large for the correlation kernel");
+    if (2 * (size_t)c->pitch * 4 > ISING_MAX_CORR_ROW_BYTES) return fail(ISING_ESTATE, "X too large for the correlation kernel");
     if (int rc = ising_sync(c)) return rc;
     CorrParams p{};
     for (int i = 0; i < n; i++) { p.black[i] = local_row(c, c->dev[i], 0, 0); p.white[i] = local_row(c, c->dev[i], 1, 0); }
@@ -529,7 +564,8 @@ int ising_update_color(ising_ctx* c, int color, int it)
         // edge tile rows first, in the kernel variant that stores them into the neighbours' ghost
         // rows; the interior follows on the same stream in the plain variant (measured 1-2 % faster
         // per launch than one kernel carrying the push code for every CTA)
-        const bool split = c->cfg.Y / TH > 2;
+        // (one-CTA-per-tile kernel only; the persistent kernel walks the edge tile rows first in ONE launch)
+        const bool split = !c->persistent && c->split_edges && c->cfg.Y / TH > 2;
         for (int i = 0; i < (int)c->dev.size(); i++) {
             if (int rc = launch_part(c, i, color, it, split ? ISING_PART_EDGES : ISING_PART_ALL, c->dev[i].stream)) return rc;
             if (split)
@@ -605,6 +641,9 @@ int ising_update_color_part(ising_ctx* c, int dev, int color, int it, int part, 
 {
     if (!c || dev < 0 || dev >= (int)c->dev.size() || (color != 0 && color != 1) || part < 0 || part > 2)
         return fail(ISING_EINVAL, "bad argument");
+    // a partial launch on a fused context would push without being counted in pushes_done: every later
+    // wait value would be too small and the ghost-row ordering silently lost
+    if (c->fused) return fail(ISING_ESTATE, "ising_update_color_part is not valid on a context with the fused halo push; use ising_update_color");
     return launch_part(c, dev, color, it, part, stream ? (cudaStream_t)stream : c->dev[dev].stream);
 }
 
@@ -625,6 +664,14 @@ int ising_sync(ising_ctx* c)
         CU_TRY(cudaSetDevice(d.device));
         CU_TRY(cudaStreamSynchronize(d.stream));
     }
+    if (c->fused)   // a bounded wait on a neighbour's arrival counter gave up: the lattice is not valid any more
+        for (DevState& d : c->dev) {
+            unsigned int err = 0;
+            CU_TRY(cudaSetDevice(d.device));
+            CU_TRY(cudaMemcpy(&err, d.d_flags + ERR_FLAG_WORD, sizeof(err), cudaMemcpyDeviceToHost));
+            if (err) return fail(ISING_ETIMEOUT, "device %d: halo rows of a neighbouring slab did not arrive within %.1f s",
+                                 d.device, (double)c->spin_timeout_ns * 1e-9);
+        }
     return ISING_OK;
 }
 
@@ -681,12 +728,22 @@ int ising_count_spins(ising_ctx* c, uint64_t* up, uint64_t* down)
 int ising_bond_sum(ising_ctx* c, int64_t* bond_sum)
 {
     if (!c || !bond_sum) return fail(ISING_EINVAL, "bad argument");
-    if (c->ghost_rows && !c->peer_halo)
-        ;   // caller-managed ghost rows: they are current after any complete sweep + exchange
+    // Ghost rows: bond_differ_kernel reads the WHITE ghost rows, which the neighbouring slabs write.
+    //   fused push  : their stores are ordered by the arrival counters only -> wait for the counters on
+    //                 this device's stream first (covers peer-access and IPC neighbours alike);
+    //   copy mode   : push_halo() already made this stream wait for the neighbours' copies;
+    //   caller-managed (ISING_F_NO_PEER_COPY without attach): current after the caller's own exchange.
     uint64_t differ = 0;
     for (int i = 0; i < (int)c->dev.size(); i++) {
         DevState& d = c->dev[i];
         CU_TRY(cudaSetDevice(d.device));
+        if (c->ghost_rows && c->fused) {
+            const unsigned int tiles_x = (unsigned int)(c->pitch / TW);
+            launch_halo_wait(d.d_flags, (unsigned int)(c->pushes_done[0] * tiles_x), (unsigned int)(c->pushes_done[1] * tiles_x),
+                             d.d_flags + ERR_FLAG_WORD, c->spin_timeout_ns, d.stream);
+            CU_TRY(cudaGetLastError());
+            c->launches++;
+        }
         CU_TRY(cudaMemsetAsync(d.d_counts + 1, 0, sizeof(unsigned long long), d.stream));
         launch_bond_differ(local_row(c, d, 0, 0), local_row(c, d, 1, 0), c->cfg.Y, c->pitch, c->yperiod, c->xperiod,
                            (uint32_t)(c->cfg.slab_first + i) * (uint32_t)c->cfg.Y, d.d_counts + 1, d.stream);
@@ -746,13 +803,16 @@ int ising_import_bits(ising_ctx* c, int dev, const uint32_t* black, const uint32
 namespace {
 struct CkptHeader {
     char magic[8];          // "ISB200CK"
-    uint32_t version;       // 1
+    uint32_t version;       // 2 (1 had no flags / j_prob)
     int32_t X, Y, ndev, xsl, ysl, slab_first, slab_count;
     uint64_t seed;
-    float temp;
-    uint32_t pad;
+    float temp;             // temperature in force when the checkpoint was written (restored on load)
+    float j_prob;           // -J probability (the bond planes are regenerated from seed + 1 and this)
     uint64_t iterations;    // sweeps done; the next sweep uses it = iterations + 1
+    int32_t flags;          // ISING_F_BONDS of the writing context
+    int32_t pad;
 };
+constexpr uint32_t CKPT_VERSION = 2;
 }  // namespace
 
 int ising_save_checkpoint(ising_ctx* c, const char* path, uint64_t iterations_done)
@@ -762,7 +822,8 @@ int ising_save_checkpoint(ising_ctx* c, const char* path, uint64_t iterations_do
     if (!fp) return fail(ISING_EINVAL, "cannot open %s for writing", path);
     CkptHeader h{};
     memcpy(h.magic, "ISB200CK", 8);
-    h.version = 1;
+    h.version = CKPT_VERSION;
+    h.flags = c->cfg.flags & ISING_F_BONDS; h.j_prob = c->bonds ? c->cfg.j_prob : 0.f;
     h.X = c->cfg.X; h.Y = c->cfg.Y; h.ndev = (int32_t)c->dev.size(); h.xsl = c->cfg.xsl; h.ysl = c->cfg.ysl;
     h.slab_first = c->cfg.slab_first; h.slab_count = c->slab_count; h.seed = c->cfg.seed; h.temp = c->cfg.temp;
     h.iterations = iterations_done;
@@ -783,9 +844,20 @@ int ising_load_checkpoint(ising_ctx* c, const char* path, uint64_t* iterations_d
     FILE* fp = fopen(path, "rb");
     if (!fp) return fail(ISING_EINVAL, "cannot open %s", path);
     CkptHeader h{};
-    if (fread(&h, sizeof(h), 1, fp) != 1 || memcmp(h.magic, "ISB200CK", 8) != 0 || h.version != 1) {
+    if (fread(&h, sizeof(h), 1, fp) != 1 || memcmp(h.magic, "ISB200CK", 8) != 0) {
         fclose(fp);
         return fail(ISING_EINVAL, "%s is not an ising_b200 checkpoint", path);
+    }
+    if (h.version != CKPT_VERSION) {
+        fclose(fp);
+        return fail(ISING_EINVAL, "%s is a version %u checkpoint, this library reads version %u", path, h.version, CKPT_VERSION);
+    }
+    // the Hamiltonian must be the one the run was started with: same -J flag and probability
+    if (h.flags != (c->cfg.flags & ISING_F_BONDS) || (c->bonds && h.j_prob != c->cfg.j_prob)) {
+        fclose(fp);
+        return fail(ISING_EINVAL, "checkpoint %s was written %s random bonds (p = %g), this context runs %s (p = %g)", path,
+                    h.flags ? "with" : "without", (double)h.j_prob, c->bonds ? "with" : "without",
+                    (double)(c->bonds ? c->cfg.j_prob : 0.f));
     }
     if (h.X != c->cfg.X || h.Y != c->cfg.Y || h.ndev != (int32_t)c->dev.size() || h.slab_first != c->cfg.slab_first ||
         h.slab_count != c->slab_count || h.xsl != c->cfg.xsl || h.ysl != c->cfg.ysl) {
@@ -813,6 +885,9 @@ int ising_load_checkpoint(ising_ctx* c, const char* path, uint64_t* iterations_d
     }
     fclose(fp);
     if (iterations_done) *iterations_done = h.iterations;
+    // the run continues under the temperature it was saved at (a -u ramp may have moved it since the start)
+    if (h.temp != c->cfg.temp)
+        if (int rc = ising_set_temperature(c, h.temp)) return rc;
     return refresh_ghosts_after_import(c);   // all devices are loaded: boundary rows -> neighbours' ghost rows
 }
 
@@ -949,7 +1024,7 @@ static int run_batch(ising_ctx* ctx_a, ising_ctx* ctx_b, int nrep, const uint32_
             // the ghost rows are overwritten from the host
             const unsigned int tiles_x = (unsigned int)(c->pitch / TW);
             launch_halo_wait(d.d_flags, (unsigned int)(c->pushes_done[0] * tiles_x), (unsigned int)(c->pushes_done[1] * tiles_x),
-                             d.stream);
+                             d.d_flags + ERR_FLAG_WORD, c->spin_timeout_ns, d.stream);
             c->launches++;
             e = cudaGetLastError();
             // Only the WHITE ghost rows come from the host: the first colour step (black) reads nothing else,

@@ -54,6 +54,33 @@ __device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int* p)
     return v;
 }
 
+__device__ __forceinline__ unsigned long long global_timer_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+// Spin until *flag has reached `want` (wrap-safe), but never longer than timeout_ns: a neighbour that
+// died or hangs must not hang this GPU.  On timeout the error word is set (ising_sync reports it) and
+// the caller goes on with whatever the ghost row holds.
+__device__ __noinline__ void bounded_wait_counter(const unsigned int* flag, unsigned int want, unsigned int* err_flag,
+                                                  unsigned long long timeout_ns)
+{
+    if ((int)(ld_acquire_sys(flag) - want) >= 0) return;
+    const unsigned long long t0 = global_timer_ns();
+    unsigned int polls = 0;
+    while ((int)(ld_acquire_sys(flag) - want) < 0) {
+        if ((++polls & 1023u) == 0 && global_timer_ns() - t0 > timeout_ns) {
+            if (err_flag) atomicExch_system(err_flag, 1u);
+            return;
+        }
+    }
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
 // acc |= (x > thr) << BIT as one compare and one predicated OR-immediate.
 __device__ __forceinline__ void or_bit_if_gt(uint32_t& acc, uint32_t x, uint32_t thr, int bit)
 {
@@ -82,6 +109,24 @@ __device__ __forceinline__ void philox_call(int q, const ThreadConsts& tc, uint3
     else if (f0)   philox_fast_mix<false, true>(tc, ta, tb, td, k0, k1, out);
     else if (f1)   philox_fast_mix<true, false>(tc, ta, tb, td, k0, k1, out);
     else           philox_fast(tc, ta, tb, td, k0, k1, out);
+}
+
+// Fused halo push of an edge tile (called by the CTAs that own the slab's first / last row only): the
+// half-warps holding row 0 / Y-1 store their new words a second time into the neighbour's ghost row
+// (peer-mapped), make them visible system-wide and count the tile on the neighbour's arrival counter.
+// Out of line so that the code and registers of the push do not weigh on the CTAs that never push.
+__device__ __noinline__ void push_edge_rows(const UpdateParams& p, int x0, int y0, uint32_t me0, uint32_t me1)
+{
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    const int row = y0 + ty;
+    const bool top = (row == 0), bot = (row == p.rows - 1);
+    if (top) { p.push_up[x0 + tx] = me0; p.push_up[x0 + tx + 16] = me1; }
+    if (bot) { p.push_dn[x0 + tx] = me0; p.push_dn[x0 + tx + 16] = me1; }
+    if (top || bot) __threadfence_system();
+    __syncwarp();
+    // rows 0 and Y-1 are written by the half-warps ty == 0 (threads 0..15) and ty == 15 (240..255)
+    if (top && tx == 0) atomicAdd_system(p.sig_up, 1u);
+    if (bot && tx == 0) atomicAdd_system(p.sig_dn, 1u);
 }
 
 // Reject masks of one 32-site word: 8 Philox calls, outputs x,y,z,w -> bits 2q, 16+2q, 2q+1,
@@ -207,8 +252,8 @@ update_color_kernel(const __grid_constant__ CUtensorMap src_tile, const __grid_c
     me[1] = my[16];
     if (threadIdx.x == 0) {
         if (PUSH) {   // ghost rows of the source colour must have arrived from the neighbours
-            if (y0 == 0) while ((int)(ld_acquire_sys(p.wait_top) - p.wait_value) < 0) { }
-            if (y0 + TH == p.rows) while ((int)(ld_acquire_sys(p.wait_bot) - p.wait_value) < 0) { }
+            if (y0 == 0) bounded_wait_counter(p.wait_top, p.wait_value, p.err_flag, p.spin_timeout_ns);
+            if (y0 + TH == p.rows) bounded_wait_counter(p.wait_bot, p.wait_value, p.err_flag, p.spin_timeout_ns);
             asm volatile("fence.proxy.async;" ::: "memory");   // later TMA reads see the peer's stores
         }
         int ytop, ybot;
@@ -273,32 +318,248 @@ update_color_kernel(const __grid_constant__ CUtensorMap src_tile, const __grid_c
         my[16 * j] = me[j];
     }
     if (PUSH && (y0 == 0 || y0 + TH == p.rows)) {   // CTA-uniform: only the two edge tile rows push
-        const int row = y0 + ty;
-        const bool top = (row == 0), bot = (row == p.rows - 1);
-        if (top) { p.push_up[x0 + tx] = me[0]; p.push_up[x0 + tx + 16] = me[1]; }
-        if (bot) { p.push_dn[x0 + tx] = me[0]; p.push_dn[x0 + tx + 16] = me[1]; }
-        if (top || bot) __threadfence_system();
-        __syncwarp();
-        // rows 0 and Y-1 are written by the half-warps ty == 0 (threads 0..15) and ty == 15 (240..255)
-        if (top && tx == 0) atomicAdd_system(p.sig_up, 1u);
-        if (bot && tx == 0) atomicAdd_system(p.sig_dn, 1u);
+        push_edge_rows(p, x0, y0, me[0], me[1]);
     }
 }
 
 // Wait until the neighbours' fused halo pushes have all arrived: flags[0], flags[2] (top / bottom ghost row
 // of colour 0) must have reached want0, flags[1], flags[3] want1.  Put on a stream ahead of anything that
 // overwrites the ghost rows (host upload of the next replica).
-__global__ void halo_wait_kernel(const unsigned int* flags, unsigned int want0, unsigned int want1)
+__global__ void halo_wait_kernel(const unsigned int* flags, unsigned int want0, unsigned int want1,
+                                 unsigned int* err_flag, unsigned long long timeout_ns)
 {
     if (threadIdx.x < 4) {
         const unsigned int want = (threadIdx.x & 1) ? want1 : want0;
-        while ((int)(ld_acquire_sys(flags + threadIdx.x) - want) < 0) { }
+        bounded_wait_counter(flags + threadIdx.x, want, err_flag, timeout_ns);
     }
 }
 
-void launch_halo_wait(const unsigned int* flags, unsigned int want0, unsigned int want1, cudaStream_t stream)
+void launch_halo_wait(const unsigned int* flags, unsigned int want0, unsigned int want1, unsigned int* err_flag,
+                      unsigned long long timeout_ns, cudaStream_t stream)
 {
-    halo_wait_kernel<<<1, 32, 0, stream>>>(flags, want0, want1);
+    halo_wait_kernel<<<1, 32, 0, stream>>>(flags, want0, want1, err_flag, timeout_ns);
+}
+
+
+// ------------------------------------------------------------------------------------------
+// Persistent colour half-sweep (the product kernel).  Same tile, same thread <-> reference-thread-id
+// map and same arithmetic as update_color_kernel, but one CTA per resident slot (SMs x 4) walks over
+// the tiles  blockIdx.x + k * gridDim.x  of the launch:
+//   * everything that is per launch or per thread (parameters, read_back, the thread's offset in a
+//     tile, barrier set-up) is paid once per CTA lifetime instead of once per 64 sites x 256 threads;
+//     the old kernel spent ~27 % of its stall samples in its first 31 instructions;
+//   * the tiles (source colour + halo + the tile being updated) arrive through an 8-stage shared-memory
+//     ring: one lane of warp k mod 8 issues the six TMA boxes of tile k+4 at the top of iteration k
+//     (full[] / empty[] mbarriers, no CTA-wide barrier in the loop, warps drift freely by up to four tiles);
+//   * with edges_first the two edge tile rows of a slab are the first tiles of the walk, so the fused
+//     halo push (PUSH) leaves in the first iteration of CTAs 0 .. 2*tiles_x-1 of the SAME launch that
+//     does the interior -- no separate 64-CTA edge launch in front of the interior any more.
+// ------------------------------------------------------------------------------------------
+struct alignas(128) TileStage {
+    uint32_t v[(TH + 2) * TW];   // source colour, rows: above, 16 centre rows, below
+    uint32_t l[TH * SIDE_W];
+    uint32_t r[TH * SIDE_W];
+    uint32_t own[TH * TW];       // the tile being updated (a global load in the loop was sunk next to its use
+                                 // by the compiler and showed up as long-scoreboard stalls)
+};
+
+__device__ __forceinline__ int sched_tile_row(int r, const UpdateParams& p)
+{
+    if (p.edges_first) return (r == 0) ? p.tile_row0 : ((r == 1) ? p.tile_row_alt : r - 1);
+    return p.tile_row0 + r;
+}
+
+// Warp 0, converged: arm full[stage] and issue the five TMA boxes of the tile (tile_row, col).
+// Lanes 0..3 each take one of the four wrap tests so that the warp pays for one division.
+template <bool PUSH>
+__device__ __forceinline__ void produce_tile(TileStage* st, uint64_t* full, const CUtensorMap* src_tile,
+                                             const CUtensorMap* src_row, const CUtensorMap* src_side,
+                                             const CUtensorMap* dst_tile, const UpdateParams& p, int tile_row,
+                                             int col, int lane)
+{
+    const int x0 = col * TW, y0 = tile_row * TH;
+    unsigned int n = 0, d = 1;
+    if (lane == 0) { n = (unsigned)x0; d = (unsigned)p.xperiod; }
+    if (lane == 1) { n = (unsigned)(x0 + TW); d = (unsigned)p.xperiod; }
+    if (p.yperiod > 0) {
+        if (lane == 2) { n = (unsigned)y0; d = (unsigned)p.yperiod; }
+        if (lane == 3) { n = (unsigned)(y0 + TH); d = (unsigned)p.yperiod; }
+    }
+    const unsigned int wrap = __ballot_sync(0xffffffffu, (n % d) == 0u);
+    if (lane == 0) {
+        if (PUSH) {   // ghost rows of the source colour must have arrived from the neighbours
+            if (y0 == 0) bounded_wait_counter(p.wait_top, p.wait_value, p.err_flag, p.spin_timeout_ns);
+            if (y0 + TH == p.rows) bounded_wait_counter(p.wait_bot, p.wait_value, p.err_flag, p.spin_timeout_ns);
+            asm volatile("fence.proxy.async;" ::: "memory");   // later TMA reads see the peer's stores
+        }
+        int ytop = y0 - 1, ybot = y0 + TH;     // ghost rows when yperiod == 0
+        if (p.yperiod > 0) {
+            if (wrap & 4u) ytop = y0 + p.yperiod - 1;
+            if (wrap & 8u) ybot = y0 + TH - p.yperiod;
+        }
+        const int xl = (wrap & 1u) ? x0 + p.xperiod - 1 : x0 - 1;
+        const int xr = (wrap & 2u) ? x0 + TW - p.xperiod : x0 + TW;
+        constexpr uint32_t bytes = ((TH + 2) * TW + 2 * TH * SIDE_W + TH * TW) * 4;
+        mbar_expect_tx(full, bytes);
+        // allocation row = local row + 1 (row 0 of the allocation is the upper ghost row)
+        tma_load_2d(st->v + TW, src_tile, x0, y0 + 1, full);
+        tma_load_2d(st->own, dst_tile, x0, y0 + 1, full);
+        tma_load_2d(st->v, src_row, x0, ytop + 1, full);
+        tma_load_2d(st->v + (TH + 1) * TW, src_row, x0, ybot + 1, full);
+        tma_load_2d(st->l, src_side, xl - (SIDE_W - 1), y0 + 1, full);
+        tma_load_2d(st->r, src_side, xr, y0 + 1, full);
+    }
+    __syncwarp();
+}
+
+template <bool FAST, bool BONDS, bool PUSH>
+__global__ void __launch_bounds__(UPDATE_THREADS, ISING_MIN_BLOCKS)
+update_color_persistent(const __grid_constant__ CUtensorMap src_tile, const __grid_constant__ CUtensorMap src_row,
+                        const __grid_constant__ CUtensorMap src_side, const __grid_constant__ CUtensorMap dst_tile,
+                        uint32_t* __restrict__ dst /* local row 0 */,
+                        const uint32_t* __restrict__ bonds /* 4 planes: up, down, left, right; local row 0 */,
+                        const __grid_constant__ UpdateParams p)
+{
+    __shared__ TileStage stage[UPDATE_STAGES];
+    __shared__ alignas(8) uint64_t full[UPDATE_STAGES];    // TMA bytes of the stage have landed
+    __shared__ alignas(8) uint64_t empty[UPDATE_STAGES];   // all 8 warps have read the stage
+
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int G = (int)gridDim.x;
+
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int s = 0; s < UPDATE_STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], UPDATE_THREADS / 32); }
+        fence_mbar_init();
+    }
+    __syncthreads();   // once per CTA lifetime
+
+    // consumer walk (tile of iteration k) and producer walk (tile of iteration k + UPDATE_PREFETCH)
+    int t = (int)blockIdx.x, r = t / p.tiles_x, col = t - r * p.tiles_x;
+    int tp = t, rp = r, colp = col;
+#pragma unroll
+    for (int i = 0; i < UPDATE_PREFETCH; i++) {   // the first tiles: one warp each
+        if (tp < p.n_tiles && warp == i)
+            produce_tile<PUSH>(&stage[i], &full[i], &src_tile, &src_row, &src_side, &dst_tile, p, sched_tile_row(rp, p), colp, lane);
+        tp += G; rp += p.step_rows; colp += p.step_cols;
+        if (colp >= p.tiles_x) { colp -= p.tiles_x; rp++; }
+    }
+
+    // per-thread constants of the walk
+    const uint32_t tid_thread = threadIdx.x;                         // (grow % 16) * 16 + c % 16
+    const uint32_t tile_row_g0 = p.grow0 / (uint32_t)TH;             // global tile row of local tile row 0
+    // side neighbour is at colour-column m-1 ("readBack", main.cu:542) or m+1; grow0 and y0 are even
+    const bool read_back = (p.color == 0) ? !(ty & 1) : (ty & 1);
+    const size_t thread_off = (size_t)ty * p.pitch + tx;
+    const bool need_b = FAST || (p.rule.selB[0] | p.rule.selB[1] | p.rule.selB[2] | p.rule.selB[3] | p.rule.selB[4]);
+
+#pragma unroll 1
+    for (int k = 0; t < p.n_tiles; k++) {
+        const int s = k & (UPDATE_STAGES - 1);
+        // ---- producer: tile of iteration k + UPDATE_PREFETCH into the stage read UPDATE_STAGES - UPDATE_PREFETCH
+        // iterations ago.  The job rotates over the warps (warp k mod 8 in iteration k): a fixed producer warp
+        // executes ~15 % more instructions than the others, falls behind, and the other seven then spin on
+        // full[] -- measured: 27 % of all stall samples, 34 polls per wait.
+        if (tp < p.n_tiles && warp == (k & (UPDATE_THREADS / 32 - 1))) {
+            const int kp = k + UPDATE_PREFETCH, sp = kp & (UPDATE_STAGES - 1);
+            if (kp >= UPDATE_STAGES) mbar_wait(&empty[sp], ((kp / UPDATE_STAGES) + 1) & 1);
+            produce_tile<PUSH>(&stage[sp], &full[sp], &src_tile, &src_row, &src_side, &dst_tile, p, sched_tile_row(rp, p), colp, lane);
+        }
+        tp += G; rp += p.step_rows; colp += p.step_cols;
+        if (colp >= p.tiles_x) { colp -= p.tiles_x; rp++; }
+
+        // ---- consumer
+        const int tile_row = sched_tile_row(r, p);
+        const int x0 = col * TW, y0 = tile_row * TH;
+        uint32_t* const my = dst + (size_t)y0 * p.pitch + x0 + thread_off;
+        uint32_t me[2];
+        uint32_t jb[2][4];
+        if (BONDS) {
+            const size_t plane = (size_t)p.bond_rows * p.pitch, off = (size_t)y0 * p.pitch + x0 + thread_off;
+#pragma unroll
+            for (int d = 0; d < 4; d++) {
+                jb[0][d] = bonds[d * plane + off];
+                jb[1][d] = bonds[d * plane + off + 16];
+            }
+        }
+        const uint32_t tid = ((tile_row_g0 + (uint32_t)tile_row) * p.grid_x + (uint32_t)col) * 256u + tid_thread;
+        const ThreadConsts tc = make_thread_consts(tid, p.st.x1, p.st.k1r3);
+
+        uint32_t rejA[2], rejB[2];
+        if (need_b) {
+            word_reject_masks<2, 0>(tc, p.st, p.rule.thrA, p.rule.thrB, rejA[0], rejB[0]);
+            word_reject_masks<2, 1>(tc, p.st, p.rule.thrA, p.rule.thrB, rejA[1], rejB[1]);
+        } else {
+            word_reject_masks<1, 0>(tc, p.st, p.rule.thrA, p.rule.thrB, rejA[0], rejB[0]);
+            word_reject_masks<1, 1>(tc, p.st, p.rule.thrA, p.rule.thrB, rejA[1], rejB[1]);
+        }
+
+        mbar_wait(&full[s], (k / UPDATE_STAGES) & 1);
+        const TileStage& st = stage[s];
+        uint32_t up[2], ct[2], dn[2], sd[2];
+#pragma unroll
+        for (int j = 0; j < 2; j++) {
+            const int w = tx + 16 * j;
+            me[j] = st.own[ty * TW + w];
+            up[j] = st.v[ty * TW + w];
+            ct[j] = st.v[(ty + 1) * TW + w];
+            dn[j] = st.v[(ty + 2) * TW + w];
+            if (read_back) {
+                const uint32_t prev = (w == 0) ? st.l[ty * SIDE_W + SIDE_W - 1] : st.v[(ty + 1) * TW + w - 1];
+                sd[j] = __funnelshift_l(prev, ct[j], 1);    // (ct << 1) | (prev >> 31)
+            } else {
+                const uint32_t next = (w == TW - 1) ? st.r[ty * SIDE_W] : st.v[(ty + 1) * TW + w + 1];
+                sd[j] = __funnelshift_r(ct[j], next, 1);    // (ct >> 1) | (next << 31)
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[s]);   // the stage is in registers: the producer may refill it
+#pragma unroll
+        for (int j = 0; j < 2; j++) {
+            if (BONDS) {   // an antiferromagnetic bond flips the neighbour's sign as seen by this site
+                up[j] ^= jb[j][0];
+                dn[j] ^= jb[j][1];
+                if (read_back) { sd[j] ^= jb[j][2]; ct[j] ^= jb[j][3]; }   // sd = left neighbour, ct = right
+                else           { ct[j] ^= jb[j][2]; sd[j] ^= jb[j][3]; }   // ct = left neighbour, sd = right
+            }
+            me[j] ^= flip_mask<FAST>(me[j], up[j], dn[j], ct[j], sd[j], rejA[j], rejB[j], p.rule);
+            my[16 * j] = me[j];
+        }
+        if (PUSH && (y0 == 0 || y0 + TH == p.rows)) {   // CTA-uniform: only the two edge tile rows push
+            push_edge_rows(p, x0, y0, me[0], me[1]);
+        }
+
+        t += G; r += p.step_rows; col += p.step_cols;
+        if (col >= p.tiles_x) { col -= p.tiles_x; r++; }
+    }
+}
+
+void launch_update_persistent(const CUtensorMap& src_tile, const CUtensorMap& src_row, const CUtensorMap& src_side,
+                              const CUtensorMap& dst_tile, uint32_t* dst, const uint32_t* bonds, UpdateParams p,
+                              int tiles_x, int tile_rows, int sms, cudaStream_t stream)
+{
+    const long long n_tiles = (long long)tiles_x * tile_rows;
+    long long grid = (long long)sms * ISING_MIN_BLOCKS;
+    if (grid > n_tiles) grid = n_tiles;
+    p.tiles_x = tiles_x;
+    p.n_tiles = (int)n_tiles;
+    p.launch_tile_rows = tile_rows;
+    p.step_rows = (int)(grid / tiles_x);
+    p.step_cols = (int)(grid % tiles_x);
+#define ISING_LAUNCH_P(F, B, P) \
+    update_color_persistent<F, B, P><<<(unsigned)grid, UPDATE_THREADS, 0, stream>>>(src_tile, src_row, src_side, dst_tile, dst, bonds, p)
+    const int sel = (p.rule.fast ? 4 : 0) | (bonds ? 2 : 0) | (p.push ? 1 : 0);
+    switch (sel) {
+        case 0: ISING_LAUNCH_P(false, false, false); break;
+        case 1: ISING_LAUNCH_P(false, false, true); break;
+        case 2: ISING_LAUNCH_P(false, true, false); break;
+        case 3: ISING_LAUNCH_P(false, true, true); break;
+        case 4: ISING_LAUNCH_P(true, false, false); break;
+        case 5: ISING_LAUNCH_P(true, false, true); break;
+        case 6: ISING_LAUNCH_P(true, true, false); break;
+        default: ISING_LAUNCH_P(true, true, true); break;
+    }
+#undef ISING_LAUNCH_P
 }
 
 // (tiles_x, tile rows) as a 3-D grid: rows beyond 32768 spill into z

@@ -52,7 +52,20 @@ struct UpdateParams {
     const unsigned int* wait_top;   // own counters for the SOURCE colour's ghost rows
     const unsigned int* wait_bot;
     unsigned int wait_value;        // pushes the neighbours must have completed: steps * tiles_x
+    unsigned int* err_flag;         // set to 1 when a bounded wait on a neighbour's counter times out
+    unsigned long long spin_timeout_ns;
+    // persistent kernel: the launch covers launch_tile_rows * tiles_x tiles, walked by every CTA with
+    // stride gridDim.x; step_rows / step_cols = gridDim.x / tiles_x, gridDim.x % tiles_x (no division
+    // in the loop).  edges_first: launch row 0 -> tile_row0, 1 -> tile_row_alt, r >= 2 -> r - 1.
+    int tiles_x;
+    int n_tiles;
+    int step_rows, step_cols;
+    int edges_first;
 };
+
+// Persistent kernel geometry: NSTAGE-deep ring of source-colour tiles in shared memory.
+constexpr int UPDATE_STAGES = 8;
+constexpr int UPDATE_PREFETCH = 4;   // tiles the TMA producer runs ahead of the consumers
 
 struct InitParams {
     StepTables st;
@@ -97,7 +110,12 @@ void launch_bond_differ(const uint32_t* black, const uint32_t* white, int rows, 
                         int xperiod, uint32_t grow0, unsigned long long* counts, cudaStream_t stream);
 void launch_to_ref(const uint32_t* plane, int rows, int pitch, unsigned long long* out, cudaStream_t stream);
 void launch_from_ref(const unsigned long long* in, int rows, int pitch, uint32_t* plane, cudaStream_t stream);
-void launch_halo_wait(const unsigned int* flags, unsigned int want0, unsigned int want1, cudaStream_t stream);
+void launch_halo_wait(const unsigned int* flags, unsigned int want0, unsigned int want1, unsigned int* err_flag,
+                      unsigned long long timeout_ns, cudaStream_t stream);
+// persistent variant of launch_update: one CTA per resident slot (sms * ctas_per_sm), tiles by stride
+void launch_update_persistent(const CUtensorMap& src_tile, const CUtensorMap& src_row, const CUtensorMap& src_side,
+                              const CUtensorMap& dst_tile, uint32_t* dst_local_row0, const uint32_t* bond_planes,
+                              UpdateParams p, int tiles_x, int tile_rows, int sms, cudaStream_t stream);
 const char* update_kernel_name(int fast);
 
 }  // namespace ising

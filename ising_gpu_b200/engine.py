@@ -62,6 +62,7 @@ def load_library():
         "ising_sync": ([vp], C.c_int),
         "ising_sweeps_timed": ([vp, C.c_int, C.c_int, C.POINTER(C.c_float)], C.c_int),
         "ising_set_temperature": ([vp, C.c_float], C.c_int),
+        "ising_get_temperature": ([vp, C.POINTER(C.c_float)], C.c_int),
         "ising_count_spins": ([vp, u64p, u64p], C.c_int),
         "ising_bond_sum": ([vp, C.POINTER(C.c_int64)], C.c_int),
         "ising_correlation": ([vp, C.c_int, C.POINTER(C.c_double)], C.c_int),
@@ -117,7 +118,7 @@ def load_library():
 
 EXPORTED_SYMBOLS = ("ising_create ising_destroy ising_last_error ising_abi_version ising_set_stream "
                     "ising_init_lattice ising_update_color ising_sweeps ising_sync ising_sweeps_timed "
-                    "ising_set_temperature ising_count_spins ising_bond_sum ising_correlation "
+                    "ising_set_temperature ising_get_temperature ising_count_spins ising_bond_sum ising_correlation "
                     "ising_export_bonds_ref_layout ising_export_ref_layout "
                     "ising_import_ref_layout ising_export_bits ising_import_bits ising_dump_lattice "
                     "ising_save_checkpoint ising_load_checkpoint "

@@ -91,3 +91,24 @@ def test_numa_binding_is_a_no_op_without_a_gpu():
     before = os.sched_getaffinity(0)
     assert bind_process_near_gpu(0) is None
     assert os.sched_getaffinity(0) == before
+
+
+def test_shipped_kernels_are_blackwell_native():
+    """cuobjdump of the built library: the update kernels stage tiles with TMA (UTMALDG) behind mbarriers (SYNCS), the
+    tensor-core variant issues tcgen05.mma kind::i8 (UTCIMMA) and reads TMEM with tcgen05.ld (LDTM).  The same
+    histograms are committed under profiles/sass_opcodes_*.txt by __graft_entry__.build()."""
+    import shutil
+    import sys
+    if not shutil.which("cuobjdump"):
+        pytest.skip("cuobjdump not on PATH")
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import sass_histogram
+    hs = sass_histogram.histograms()
+    for tag, need in sass_histogram.MUST.items():
+        assert tag in hs, tag
+        for op in need:
+            assert any(k.startswith(op) for k in hs[tag]["ops"]), (tag, op)
+    assert hs["tc_update_pipe_kernel"]["ops"]["UTCIMMA"] >= 8
+    assert hs["update_color_kernel_fast"]["ops"]["UTMALDG"] == 5
+    # no mma.sync / wgmma fallbacks anywhere in the variant kernel
+    assert not any(k.startswith(("HMMA", "IMMA")) for k in hs["tc_update_pipe_kernel"]["ops"])
