@@ -73,6 +73,9 @@ struct DevState {
     unsigned int* dn_flags = nullptr;
     void* ipc_opened[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     int sms = 148;                             // multiprocessors: the persistent update kernel runs sms x 4 CTAs
+    // fused push: the two edge tile rows run on their own high-priority stream next to the interior launch
+    cudaStream_t stream_edge = nullptr;
+    cudaEvent_t ev_pre = nullptr, ev_edge = nullptr;
     cudaEvent_t ev_color = nullptr;            // kernel + halo pushes of the last colour issued
     cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;
 };
@@ -86,7 +89,8 @@ struct ising_ctx {
     bool bonds = false;
     bool fused = false;       // halo rows are pushed by the update kernel itself (peer stores + counters)
     bool persistent = false;  // ISING_B200_KERNEL=persistent selects the persistent kernel (A/B; measured 3 % slower)
-    bool split_edges = true;  // tile kernel, fused push: edge tile rows in their own launch ahead of the interior
+    bool split_edges = true;  // tile kernel, fused push: edge tile rows in their own launch, not inside the interior's
+    bool edge_stream = true;  // ... and that launch on a second, high-priority stream, concurrent with the interior
     unsigned long long spin_timeout_ns = 30ull * 1000000000ull;   // bound of every device-side wait on a neighbour
     uint64_t pushes_done[2] = {0, 0};
     bool peer_halo = false;   // library copies boundary rows between its own devices
@@ -318,6 +322,7 @@ int ising_create(const ising_cfg* cfg, ising_ctx** out)
     c->dev.resize(cfg->ndev);
     if (const char* k = getenv("ISING_B200_KERNEL")) c->persistent = strcmp(k, "persistent") == 0;
     if (const char* k = getenv("ISING_B200_SPLIT_EDGES")) c->split_edges = atoi(k) != 0;
+    if (const char* k = getenv("ISING_B200_EDGE_STREAM")) c->edge_stream = atoi(k) != 0;
     if (const char* t = getenv("ISING_B200_SPIN_TIMEOUT_MS")) {
         const long long ms = atoll(t);
         if (ms > 0) c->spin_timeout_ns = (unsigned long long)ms * 1000000ull;
@@ -363,6 +368,12 @@ int ising_create(const ising_cfg* cfg, ising_ctx** out)
         }
         if ((e = cudaMalloc(&d.d_counts, 2 * sizeof(unsigned long long))) != cudaSuccess) return cleanup(fail(ISING_ENOMEM, "%s", cudaGetErrorString(e)));
         if (c->ghost_rows) {
+            int prio_lo = 0, prio_hi = 0;
+            cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+            if ((e = cudaStreamCreateWithPriority(&d.stream_edge, cudaStreamNonBlocking, prio_hi)) != cudaSuccess ||
+                (e = cudaEventCreateWithFlags(&d.ev_pre, cudaEventDisableTiming)) != cudaSuccess ||
+                (e = cudaEventCreateWithFlags(&d.ev_edge, cudaEventDisableTiming)) != cudaSuccess)
+                return cleanup(fail(ISING_ECUDA, "edge stream: %s", cudaGetErrorString(e)));
             if ((e = cudaMalloc(&d.d_flags, FLAG_WORDS * sizeof(unsigned int))) != cudaSuccess ||
                 (e = cudaMemsetAsync(d.d_flags, 0, FLAG_WORDS * sizeof(unsigned int), d.stream)) != cudaSuccess)
                 return cleanup(fail(ISING_ENOMEM, "flags: %s", cudaGetErrorString(e)));
@@ -406,6 +417,9 @@ int ising_destroy(ising_ctx* c)
         if (d.d_corr) cudaFree(d.d_corr);
         if (d.d_flags) cudaFree(d.d_flags);
         for (void* q : d.ipc_opened) if (q) cudaIpcCloseMemHandle(q);
+        if (d.stream_edge) { cudaStreamSynchronize(d.stream_edge); cudaStreamDestroy(d.stream_edge); }
+        if (d.ev_pre) cudaEventDestroy(d.ev_pre);
+        if (d.ev_edge) cudaEventDestroy(d.ev_edge);
         if (d.ev_color) cudaEventDestroy(d.ev_color);
         if (d.ev_t0) cudaEventDestroy(d.ev_t0);
         if (d.ev_t1) cudaEventDestroy(d.ev_t1);
@@ -561,15 +575,30 @@ int ising_update_color(ising_ctx* c, int color, int it)
 {
     if (!c || (color != 0 && color != 1)) return fail(ISING_EINVAL, "bad argument");
     if (c->fused) {
-        // edge tile rows first, in the kernel variant that stores them into the neighbours' ghost
-        // rows; the interior follows on the same stream in the plain variant (measured 1-2 % faster
-        // per launch than one kernel carrying the push code for every CTA)
-        // (one-CTA-per-tile kernel only; the persistent kernel walks the edge tile rows first in ONE launch)
+        // Tile kernel: the two edge tile rows (64 CTAs at X = 65536) run in the kernel variant that stores them into
+        // the neighbours' ghost rows; the interior runs in the plain variant (one kernel carrying the push code for
+        // every CTA measured 1.2 % slower per launch).  Both read only what the previous colour step wrote, so they
+        // are independent of each other: the edge launch goes to a second, high-priority stream and the interior
+        // grid fills the SMs next to it -- launched back to back on one stream the GPU idled at < 11 % occupancy
+        // for one CTA lifetime (~10 us) twice per sweep (round-1 verdict: the whole 1.6 % lost at 8 GPUs).
+        // The persistent kernel walks the edge tile rows first inside ONE launch.
         const bool split = !c->persistent && c->split_edges && c->cfg.Y / TH > 2;
         for (int i = 0; i < (int)c->dev.size(); i++) {
-            if (int rc = launch_part(c, i, color, it, split ? ISING_PART_EDGES : ISING_PART_ALL, c->dev[i].stream)) return rc;
-            if (split)
-                if (int rc = launch_part(c, i, color, it, ISING_PART_INTERIOR, c->dev[i].stream)) return rc;
+            DevState& d = c->dev[i];
+            if (!split) {
+                if (int rc = launch_part(c, i, color, it, ISING_PART_ALL, d.stream)) return rc;
+            } else if (!c->edge_stream || !d.stream_edge) {
+                if (int rc = launch_part(c, i, color, it, ISING_PART_EDGES, d.stream)) return rc;
+                if (int rc = launch_part(c, i, color, it, ISING_PART_INTERIOR, d.stream)) return rc;
+            } else {
+                CU_TRY(cudaSetDevice(d.device));
+                CU_TRY(cudaEventRecord(d.ev_pre, d.stream));                 // everything issued so far, incl. the previous
+                CU_TRY(cudaStreamWaitEvent(d.stream_edge, d.ev_pre, 0));     // colour step's interior
+                if (int rc = launch_part(c, i, color, it, ISING_PART_EDGES, d.stream_edge)) return rc;
+                CU_TRY(cudaEventRecord(d.ev_edge, d.stream_edge));
+                if (int rc = launch_part(c, i, color, it, ISING_PART_INTERIOR, d.stream)) return rc;
+                CU_TRY(cudaStreamWaitEvent(d.stream, d.ev_edge, 0));         // whatever follows on the main stream sees both
+            }
         }
         c->pushes_done[color]++;
         return ISING_OK;

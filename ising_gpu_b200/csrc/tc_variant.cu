@@ -153,11 +153,11 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr)
     return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) |
            (2ull << 61);
 }
-__host__ __device__ constexpr uint32_t IDESC_I8(int a_mn_major, int b_mn_major)
+__host__ __device__ constexpr uint32_t IDESC_I8(int a_mn_major, int b_mn_major, int n = SUBN)
 {
     return (2u << 4) /* D = S32 */ | (1u << 7) /* A = INT8 */ | (1u << 10) /* B = INT8 */ |
-           ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) | ((uint32_t)(SUBN >> 3) << 17) |
-           ((uint32_t)(SUBN >> 4) << 24);
+           ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) | ((uint32_t)(n >> 3) << 17) /* N */ |
+           ((uint32_t)(SUBN >> 4) << 24) /* M */;
 }
 __device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate)
 {
@@ -445,17 +445,34 @@ constexpr int PIPE_GROUP_WARPS = ISING_TC_GROUP_WARPS;
 constexpr int PIPE_COLS = SUBN / (PIPE_GROUP_WARPS / 4);   // columns per consumer thread
 constexpr int PIPE_GROUPS = ISING_TC_GROUPS;            // consumer groups; group g takes the CTA's tiles g, g + G, ...
 constexpr int PIPE_CONSUMER_WARPS = PIPE_GROUP_WARPS * PIPE_GROUPS;
-constexpr int PIPE_THREADS = 32 * (PIPE_CONSUMER_WARPS + 1);
+// two single-thread service warps behind the consumers: warp PIPE_CONSUMER_WARPS issues the MMAs, the next one the
+// TMA loads.  One warp doing both had ~2.2 us of serial work per tile (wait for the MMAs to finish, refill, wait,
+// issue) against a tile budget of 2.5 us -- the consumers' 21 % wait at mma[] was a wait for that thread.
+constexpr int PIPE_THREADS = 32 * (PIPE_CONSUMER_WARPS + 2);
 constexpr int PIPE_STAGES = 4;                          // operand stages = TMEM accumulators (4 x 128 = all 512 columns)
-constexpr size_t PIPE_SMEM = (size_t)TILE_BYTES * (1 + 2 * PIPE_STAGES) + 1024;
+// stage = H tile, V tile, then one 1024-byte swizzle atom whose first row (row 128 of V) receives the edge row of the
+// vertically neighbouring block: a fifth k-step of the Kv x V product adds it on the tensor core (selector matrix E)
+constexpr int PIPE_STAGE_BYTES = 2 * TILE_BYTES + 1024;
+constexpr size_t PIPE_SMEM = (size_t)2 * TILE_BYTES + (size_t)PIPE_STAGES * PIPE_STAGE_BYTES + 4096 + 1024;
 static_assert(PIPE_STAGES * SUBN <= 512, "TMEM has 512 columns");
-// registers are allocated per 4 warps: 17 warps count as 20 -> 65536 / (20 * 32) = 102 -> 96 per thread;
+// registers are allocated per 4 warps: 18 warps count as 20 -> 65536 / (20 * 32) = 102 -> 96 per thread;
 // 25 warps count as 28 -> 73 -> 72 per thread
 constexpr int PIPE_MAXREG = (PIPE_CONSUMER_WARPS <= 16) ? 96 : 72;
 // with 96 registers and 64 columns per thread the tile's own spins are prefetched into registers one tile
 // ahead; otherwise they are prefetched into L2 and loaded at the start of the tile
 constexpr bool PIPE_REG_PREFETCH = (PIPE_MAXREG == 96 && PIPE_COLS == 64);
 constexpr int PIPE_CHUNKS = PIPE_COLS / 16;             // 16-byte chunks = TMEM column groups per thread
+// Build option (off): hand the accumulators over per COLUMN HALF -- every tile multiplied as two M=128, N=64
+// products with their own mma[] / free[] barriers, so that a warp only waits for the three other warps that share
+// its 64 columns.  Measured SLOWER (1013 vs 1085 updates/ns, profiles/r02_tc_variants.txt): the wait at mma[] was
+// never the 8-warp hand-over but an imbalance between the warps (see the fifth k-step of the MMA issuer), and the
+// second set of MMAs and barriers only lengthens the issuer's serial path.
+#ifndef ISING_TC_SPLIT_HALVES
+#define ISING_TC_SPLIT_HALVES 0
+#endif
+constexpr int PIPE_HALVES = (ISING_TC_SPLIT_HALVES && PIPE_GROUP_WARPS == 8) ? 2 : 1;
+constexpr int PIPE_HALF_COLS = SUBN / PIPE_HALVES;      // N of one MMA
+constexpr int PIPE_HALF_WARPS = PIPE_GROUP_WARPS / PIPE_HALVES;
 
 __device__ __forceinline__ void mbar_wait_parity(uint64_t* bar, uint32_t parity)
 {
@@ -513,9 +530,9 @@ tc_update_pipe_kernel(const __grid_constant__ CUtensorMap lat_map, const __grid_
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_addr(smem_raw) & 1023u)) & 1023u);
     uint8_t* sK = smem;                                   // the bidiagonal matrix, loaded once
-    uint8_t* sHV = smem + TILE_BYTES;                     // stage s: H at 2s, V at 2s+1 tiles
-    __shared__ __align__(16) int8_t sEdge[2 * PIPE_STAGES][SUBN];   // edge rows live one round longer than H / V
-    __shared__ __align__(8) uint64_t full_bar[PIPE_STAGES], mma_bar[PIPE_STAGES], free_bar[PIPE_STAGES], k_bar;
+    uint8_t* sE = smem + TILE_BYTES;                      // the edge-row selector matrix, loaded once
+    uint8_t* sHV = smem + 2 * TILE_BYTES;                 // stage s at s * PIPE_STAGE_BYTES: H, V, edge row (+ pad)
+    __shared__ __align__(8) uint64_t full_bar[PIPE_STAGES], mma_bar[PIPE_STAGES][PIPE_HALVES], free_bar[PIPE_STAGES][PIPE_HALVES], k_bar;
     __shared__ uint32_t tmem_base_slot;
     __shared__ __align__(16) uint32_t lut[512];           // see tc_update_mma_kernel
 
@@ -531,8 +548,10 @@ tc_update_pipe_kernel(const __grid_constant__ CUtensorMap lat_map, const __grid_
             asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr(&full_bar[s])));
             // mma[s]: one arrival from tcgen05.commit, one plain (release) arrival of the producer thread after
             // it has seen full[s] -- the consumers' only wait, which also orders the edge row for them
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], 2;" ::"r"(smem_addr(&mma_bar[s])));
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(&free_bar[s])), "r"(PIPE_GROUP_WARPS));
+            for (int hf = 0; hf < PIPE_HALVES; hf++) {
+                asm volatile("mbarrier.init.shared::cta.b64 [%0], 2;" ::"r"(smem_addr(&mma_bar[s][hf])));
+                asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(&free_bar[s][hf])), "r"(PIPE_HALF_WARPS));
+            }
         }
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr(&k_bar)));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -549,22 +568,22 @@ tc_update_pipe_kernel(const __grid_constant__ CUtensorMap lat_map, const __grid_
     const uint32_t tmem_d = tmem_base_slot;
     const int first = blockIdx.x, stride = gridDim.x;
 
-    if (warp == PIPE_CONSUMER_WARPS) {
-        // ---------------- producer: one thread drives TMA and the tensor core ----------------
+    const int nslabs = p.nby / p.nby_loc;
+    if (warp == PIPE_CONSUMER_WARPS + 1) {
+        // ---------------- loader: one thread drives TMA ---------------------------------------
         if (lane == 0) {
             asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(&k_bar)),
-                         "r"((uint32_t)TILE_BYTES)
+                         "r"((uint32_t)(2 * TILE_BYTES))
                          : "memory");
             // one bidiagonal matrix K+[r][c] = 1 for c = r, r + 1 serves all four cases: taken K-major it is
             // the "+1" operand, taken MN-major (transposed) the "-1" operand
             tma_load_rows(sK, &k_map, SUBN, &k_bar);
-            const uint32_t aK = smem_addr(sK);
+            tma_load_rows(sE, &k_map, 4 * SUBN, &k_bar);
             // operand tiles of local tile number `it` (geometry g) into stage it % PIPE_STAGES (its previous MMAs
             // have completed)
-            const int nslabs = p.nby / p.nby_loc;
             auto load_tile = [&](int it, const TileGeom& g) {
                 const int s = it & (PIPE_STAGES - 1);
-                uint8_t* sH = sHV + (2 * s) * TILE_BYTES;
+                uint8_t* sH = sHV + s * PIPE_STAGE_BYTES;
                 asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(&full_bar[s])),
                              "r"((uint32_t)(2 * TILE_BYTES + SUBN))
                              : "memory");
@@ -572,7 +591,8 @@ tc_update_pipe_kernel(const __grid_constant__ CUtensorMap lat_map, const __grid_
                 tma_load_rows(sH, &lat_map, (int)((g.sup + sub_offset(1 - g.a, g.b)) >> 7), &full_bar[s]);
                 tma_load_rows(sH + TILE_BYTES, &lat_map, (int)((g.sup + sub_offset(g.a, 1 - g.b)) >> 7), &full_bar[s]);
                 // vertical edge term (add_boundaries): last/first row of sub-block (a, 1-b) of the super-block
-                // above (b == 0) or below (b == 1), which may live in the neighbouring device's slab
+                // above (b == 0) or below (b == 1), which may live in the neighbouring device's slab.  It goes to
+                // row 128 of the V tile (swizzle phase 0 = a plain 128-byte copy), where the fifth k-step finds it.
                 int d2 = p.slab, sl2;
                 if (g.b == 0) {
                     sl2 = g.sl - 1;
@@ -584,14 +604,29 @@ tc_update_pipe_kernel(const __grid_constant__ CUtensorMap lat_map, const __grid_
                 const int8_t* edge_row = p.slab_base[d2] + (long long)(sl2 * p.nbx + g.sx) * (SUPN * SUPN) +
                                          sub_offset(g.a, 1 - g.b) + ((g.b == 0) ? (SUBN - 1) * SUBN : 0);
                 asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                                 smem_addr(sEdge[it & (2 * PIPE_STAGES - 1)])),
+                                 smem_addr(sH + 2 * TILE_BYTES)),
                              "l"(edge_row), "r"((uint32_t)SUBN), "r"(smem_addr(&full_bar[s]))
                              : "memory");
             };
-            TileWalk lw;                       // walks PIPE_STAGES tiles ahead of the MMA loop
+            TileWalk lw;
             lw.init(p, first, stride, ntiles);
             for (int k = 0; k < PIPE_STAGES; k++)
                 if (first + k * stride < ntiles) { load_tile(k, lw.geom(p)); lw.advance(); }
+            // refill stage s with tile it + PIPE_STAGES as soon as the tensor core has read tile it out of it
+            int it = 0;
+            for (int tile = first; tile + PIPE_STAGES * stride < ntiles; tile += stride, ++it) {
+                const int s = it & (PIPE_STAGES - 1);
+                const uint32_t ph = (uint32_t)(it / PIPE_STAGES) & 1u;
+                for (int hf = 0; hf < PIPE_HALVES; hf++) mbar_wait_parity(&mma_bar[s][hf], ph);
+                load_tile(it + PIPE_STAGES, lw.geom(p));
+                lw.advance();
+            }
+        }
+        __syncwarp();
+    } else if (warp == PIPE_CONSUMER_WARPS) {
+        // ---------------- MMA issuer: one thread drives the tensor core ------------------------
+        if (lane == 0) {
+            const uint32_t aK = smem_addr(sK), aE = smem_addr(sE);
             mbar_wait_parity(&k_bar, 0);
             int it = 0;
             for (int tile = first; tile < ntiles; tile += stride, ++it) {
@@ -599,27 +634,31 @@ tc_update_pipe_kernel(const __grid_constant__ CUtensorMap lat_map, const __grid_
                 const uint32_t ph = (uint32_t)(it / PIPE_STAGES) & 1u;
                 const int a = tile & 1, b = p.is_black ? a : 1 - a;   // parities of the sub-block (2nbx and ntiles are even)
                 mbar_wait_parity(&full_bar[s], ph);                               // operands landed
-                if (it >= PIPE_STAGES) mbar_wait_parity(&free_bar[s], ph ^ 1u);   // accumulator s drained by the consumers
-                asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr(&mma_bar[s])) : "memory");
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t aH = smem_addr(sHV + (2 * s) * TILE_BYTES), aV = aH + TILE_BYTES, acc = tmem_d + (uint32_t)(s * SUBN);
+                const uint32_t aH = smem_addr(sHV + s * PIPE_STAGE_BYTES), aV = aH + TILE_BYTES;
                 // k-step of a K-major operand = 32 bytes inside the 128-byte rows, of an MN-major one = 32 rows
                 const uint32_t kh_step = (a == 0) ? 4096u : 32u, kv_step = (b == 0) ? 4096u : 32u;
-                const uint32_t idesc_h = IDESC_I8(0, a == 0), idesc_v = IDESC_I8(b == 0, 1);
+                const uint32_t idesc_h = IDESC_I8(0, a == 0, PIPE_HALF_COLS), idesc_v = IDESC_I8(b == 0, 1, PIPE_HALF_COLS);
+                const uint32_t idesc_e = IDESC_I8(0, 1, PIPE_HALF_COLS);
+                // columns 64*hf .. of the B operands: 64 rows on in a K-major tile, 64 bytes on in an MN-major one
+                const uint32_t nh_step = (a == 0) ? (uint32_t)PIPE_HALF_COLS : (uint32_t)PIPE_HALF_COLS * 128u;
 #pragma unroll
-                for (int k = 0; k < 4; k++)      // H (K-major A) x Kh (B): nn[j][i] = H[j][i] + H[j][i+di]
-                    umma_i8(acc, umma_desc_sw128(aH + 32 * k), umma_desc_sw128(aK + kh_step * k), idesc_h, k > 0);
+                for (int hf = 0; hf < PIPE_HALVES; hf++) {
+                    if (it >= PIPE_STAGES) mbar_wait_parity(&free_bar[s][hf], ph ^ 1u);   // accumulator (half) drained
+                    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr(&mma_bar[s][hf])) : "memory");
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t acc = tmem_d + (uint32_t)(s * SUBN + hf * PIPE_HALF_COLS);
 #pragma unroll
-                for (int k = 0; k < 4; k++)      // Kv (A) x V (MN-major B, in place): += V[j][i] + V[j+dj][i]
-                    umma_i8(acc, umma_desc_sw128(aK + kv_step * k), umma_desc_sw128(aV + 4096 * k), idesc_v, 1u);
-                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
-                                 smem_addr(&mma_bar[s]))
-                             : "memory");
-                // refill the stage as soon as the tensor core has read it: loads run two tiles ahead
-                if (tile + PIPE_STAGES * stride < ntiles) {
-                    mbar_wait_parity(&mma_bar[s], ph);
-                    load_tile(it + PIPE_STAGES, lw.geom(p));
-                    lw.advance();
+                    for (int k = 0; k < 4; k++)      // H (K-major A) x Kh (B): nn[j][i] = H[j][i] + H[j][i+di]
+                        umma_i8(acc, umma_desc_sw128(aH + 32 * k), umma_desc_sw128(aK + kh_step * k + nh_step * hf), idesc_h, k > 0);
+#pragma unroll
+                    for (int k = 0; k < 4; k++)      // Kv (A) x V (MN-major B, in place): += V[j][i] + V[j+dj][i]
+                        umma_i8(acc, umma_desc_sw128(aK + kv_step * k), umma_desc_sw128(aV + 4096 * k + PIPE_HALF_COLS * hf), idesc_v, 1u);
+                    // fifth k-step: rows 128.. of V = the edge row (the other 31 rows meet zero columns of E):
+                    // E (K-major, slice b) x V''  adds the row above to row 0 (b == 0) or the row below to row 127
+                    umma_i8(acc, umma_desc_sw128(aE + (b == 0 ? 0u : 32u)), umma_desc_sw128(aV + 4096 * 4 + PIPE_HALF_COLS * hf), idesc_e, 1u);
+                    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                                     smem_addr(&mma_bar[s][hf]))
+                                 : "memory");
                 }
             }
         }
@@ -692,15 +731,16 @@ tc_update_pipe_kernel(const __grid_constant__ CUtensorMap lat_map, const __grid_
                 else                   l2_prefetch(gn);
             }
             const int edge_col = (g.a == 0) ? 0 : SUBN - 1;
-            // vertical edge term: a whole row, only for the first (b == 0) or last (b == 1) row of the block
-            const bool has_edge_v = (g.b == 0) ? (j == 0) : (j == SUBN - 1);
+            // (the vertical edge term -- a whole row for the first or last row of the block -- is already in the
+            // sums: the tensor core added it, see the fifth k-step of the MMA issuer)
             const uint32_t tid0 = (uint32_t)g.sb * TPS + (uint32_t)(16 * (j & 63));
             int8_t* const dst = lat + g.base + (long long)j * SUBN + colbase;
 
             // neighbour sums are in TMEM, the edge row in shared memory.  (full[s] itself must not be waited
             // on here: the producer refills the stage right after the MMAs and the barrier may already be
             // two phases ahead of a slow consumer.)
-            mbar_wait_parity(&mma_bar[s], ph);
+            const int hf = (PIPE_HALVES == 2) ? half : 0;
+            mbar_wait_parity(&mma_bar[s][hf], ph);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 
 #pragma unroll
@@ -719,20 +759,12 @@ tc_update_pipe_kernel(const __grid_constant__ CUtensorMap lat_map, const __grid_
                 // terms from across the sub-block edge (add_boundaries)
                 if (col0 == 0 && edge_col == 0) r[0] += (uint32_t)edge_h;
                 if (col0 == SUBN - 16 && edge_col == SUBN - 1) r[15] += (uint32_t)edge_h;
-                if (has_edge_v) {
-#pragma unroll
-                    for (int q4 = 0; q4 < 4; q4++) {
-                        const uint32_t e4 = *reinterpret_cast<const uint32_t*>(sEdge[it & (2 * PIPE_STAGES - 1)] + col0 + 4 * q4);
-#pragma unroll
-                        for (int q = 0; q < 4; q++) r[4 * q4 + q] += (uint32_t)(int)(int8_t)(e4 >> (8 * q));
-                    }
-                }
                 if (gq == PIPE_CHUNKS - 1) {
                     // this warp is done with accumulator s and with its edge row: hand the accumulator back
                     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                     __syncwarp();
                     if (lane == 0)
-                        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr(&free_bar[s])) : "memory");
+                        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr(&free_bar[s][hf])) : "memory");
                 }
                 uint4& w4 = own[gq];
 #pragma unroll
@@ -905,7 +937,11 @@ static int tc_create_impl(int nbx, int nby, uint64_t seed, float alpha, int firs
     EncodeFn enc = (EncodeFn)fp;
 
     // constant bidiagonal matrices
-    std::vector<int8_t> k(4 * SUBN * SUBN, 0);
+    // + a fifth tile E for the pipeline kernel's edge-row MMA: E[0][0] = 1 (k-slice 0: the row ABOVE the block
+    // lands on row 0), E[127][32] = 1 (k-slice 1: the row BELOW lands on row 127)
+    std::vector<int8_t> k(5 * SUBN * SUBN, 0);
+    k[(size_t)4 * SUBN * SUBN + 0 * SUBN + 0] = 1;
+    k[(size_t)4 * SUBN * SUBN + (SUBN - 1) * SUBN + 32] = 1;
     for (int m = 0; m < 4; m++) {
         const int d = (m & 1) ? +1 : -1;
         for (int r = 0; r < SUBN; r++) {
@@ -938,7 +974,7 @@ static int tc_create_impl(int nbx, int nby, uint64_t seed, float alpha, int firs
         // TMA maps: 128-byte rows, 128 x 128 boxes, 128-byte swizzle
         const cuuint32_t box[2] = {SUBN, SUBN}, estr[2] = {1, 1};
         const cuuint64_t strides[1] = {SUBN};
-        const cuuint64_t dl[2] = {SUBN, (cuuint64_t)(c->n_loc / SUBN)}, dk[2] = {SUBN, 4 * SUBN};
+        const cuuint64_t dl[2] = {SUBN, (cuuint64_t)(c->n_loc / SUBN)}, dk[2] = {SUBN, 5 * SUBN};
         const CUresult r1 = enc(&d.lat_map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, d.lat, dl, strides, box, estr,
                                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
