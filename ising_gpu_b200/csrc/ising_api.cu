@@ -60,6 +60,7 @@ struct DevState {
     bool own_stream = true;
     uint32_t* plane[2] = {nullptr, nullptr};   // (Y+2) x pitch words; row 0 / Y+1 are ghost rows
     CUtensorMap map_tile[2], map_row[2], map_side[2];
+    CUtensorMap map_tile2[2], map_side2[2];    // 32-row boxes of the two-tiles-per-CTA kernel
     uint32_t* bond_random = nullptr;           // 4 planes x (Y+2) x pitch (hamiltInitB_k), with edge rows
     uint32_t* bond_mirror = nullptr;           // 4 planes x Y x pitch (hamiltInitW_k)
     unsigned long long* d_corr = nullptr;
@@ -89,6 +90,7 @@ struct ising_ctx {
     bool bonds = false;
     bool fused = false;       // halo rows are pushed by the update kernel itself (peer stores + counters)
     bool persistent = false;  // ISING_B200_KERNEL=persistent selects the persistent kernel (A/B; measured 3 % slower)
+    bool two_tiles = true;    // ISING_B200_KERNEL=tile1 forces the one-tile-per-CTA kernel everywhere (A/B)
     bool split_edges = true;  // tile kernel, fused push: edge tile rows in their own launch, not inside the interior's
     bool edge_stream = true;  // ... and that launch on a second, high-priority stream, concurrent with the interior
     unsigned long long spin_timeout_ns = 30ull * 1000000000ull;   // bound of every device-side wait on a neighbour
@@ -202,7 +204,14 @@ int launch_part(ising_ctx* c, int dev, int color, int it, int part, cudaStream_t
     // hamiltInitB_k one (main.cu:1775, :1796)
     const uint32_t* bonds = nullptr;
     if (c->bonds) bonds = (color == 0) ? d.bond_mirror : d.bond_random + c->pitch;   // local row 0
-    if (c->persistent)
+    // two stacked tiles per CTA wherever the launch covers whole 32-row units of one periodic domain and needs
+    // neither bonds nor the push code (the interior of a slab, or a whole single-slab lattice)
+    const bool two = c->two_tiles && !c->persistent && !bonds && !p.push && part != ISING_PART_EDGES && (gy % 2) == 0 &&
+                     (c->yperiod == 0 || (c->yperiod % (2 * TH) == 0 && p.tile_row0 % 2 == 0));
+    if (two) p.launch_tile_rows = gy / 2;   // counted in 32-row units by that kernel
+    if (two)
+        launch_update2(d.map_tile2[src], d.map_row[src], d.map_side2[src], local_row(c, d, color, 0), p, tiles_x, gy / 2, stream);
+    else if (c->persistent)
         launch_update_persistent(d.map_tile[src], d.map_row[src], d.map_side[src], d.map_tile[color],
                                  local_row(c, d, color, 0), bonds, p, tiles_x, gy, d.sms, stream);
     else
@@ -320,7 +329,10 @@ int ising_create(const ising_cfg* cfg, ising_ctx** out)
     c->rule = make_rule(cfg->temp);
     c->thr_half = (uint32_t)(accept_count(0.5f, true) - 1);
     c->dev.resize(cfg->ndev);
-    if (const char* k = getenv("ISING_B200_KERNEL")) c->persistent = strcmp(k, "persistent") == 0;
+    if (const char* k = getenv("ISING_B200_KERNEL")) {
+        c->persistent = strcmp(k, "persistent") == 0;
+        c->two_tiles = strcmp(k, "tile1") != 0;
+    }
     if (const char* k = getenv("ISING_B200_SPLIT_EDGES")) c->split_edges = atoi(k) != 0;
     if (const char* k = getenv("ISING_B200_EDGE_STREAM")) c->edge_stream = atoi(k) != 0;
     if (const char* t = getenv("ISING_B200_SPIN_TIMEOUT_MS")) {
@@ -365,6 +377,8 @@ int ising_create(const ising_cfg* cfg, ising_ctx** out)
             if ((rc = make_map(&d.map_tile[col], d.plane[col], c->pitch, cfg->Y + 2, TW, TH))) return cleanup(rc);
             if ((rc = make_map(&d.map_row[col], d.plane[col], c->pitch, cfg->Y + 2, TW, 1))) return cleanup(rc);
             if ((rc = make_map(&d.map_side[col], d.plane[col], c->pitch, cfg->Y + 2, SIDE_W, TH))) return cleanup(rc);
+            if ((rc = make_map(&d.map_tile2[col], d.plane[col], c->pitch, cfg->Y + 2, TW, 2 * TH))) return cleanup(rc);
+            if ((rc = make_map(&d.map_side2[col], d.plane[col], c->pitch, cfg->Y + 2, SIDE_W, 2 * TH))) return cleanup(rc);
         }
         if ((e = cudaMalloc(&d.d_counts, 2 * sizeof(unsigned long long))) != cudaSuccess) return cleanup(fail(ISING_ENOMEM, "%s", cudaGetErrorString(e)));
         if (c->ghost_rows) {

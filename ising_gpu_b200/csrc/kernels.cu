@@ -81,9 +81,25 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar)
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
+// Experiment knob: bit q of ISING_ACC_ALU_MASK sends the accumulation of call q of a word to the ALU pipe (predicated
+// LOP3 xor) instead of the FMA-heavy pipe (predicated VIADD).
+#ifndef ISING_ACC_ALU_MASK
+#define ISING_ACC_ALU_MASK 0x00
+#endif
+__device__ __forceinline__ void xor_bit_if_gt(uint32_t& acc, uint32_t x, uint32_t thr, int bit)
+{
+    asm("{\n"
+        ".reg .pred p;\n"
+        "setp.gt.u32 p, %1, %2;\n"
+        "@p xor.b32 %0, %0, %3;\n"
+        "}\n"
+        : "+r"(acc)
+        : "r"(x), "r"(thr), "r"(1u << bit));
+}
 // acc |= (x > thr) << BIT as one compare and one predicated OR-immediate.
 __device__ __forceinline__ void or_bit_if_gt(uint32_t& acc, uint32_t x, uint32_t thr, int bit)
 {
+    if ((ISING_ACC_ALU_MASK >> ((bit >> 1) & 7)) & 1) { xor_bit_if_gt(acc, x, thr, bit); return; }
     asm("{\n"
         ".reg .pred p;\n"
         "setp.gt.u32 p, %1, %2;\n"
@@ -319,6 +335,162 @@ update_color_kernel(const __grid_constant__ CUtensorMap src_tile, const __grid_c
     }
     if (PUSH && (y0 == 0 || y0 + TH == p.rows)) {   // CTA-uniform: only the two edge tile rows push
         push_edge_rows(p, x0, y0, me[0], me[1]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Same colour half-sweep, two reference thread ids per thread: one CTA = 32 rows x 32 words (two stacked tiles
+// of the kernel above), thread (tx, ty) owns words tx, tx+16 of rows ty AND ty+16.  What a CTA pays once --
+// parameter and table loads (24 LDCU), barrier set-up and hand-shake, the TMA issue path of thread 0, tile
+// addressing, entry / exit -- is now spread over 128 sites per thread instead of 64, and the two Philox streams
+// of a call interleave (more independent work per warp between dependent multiplies).  Used for every launch
+// that covers an even number of 16-row tile rows without bonds and without the fused push (the interior of a
+// slab, or a whole single-slab lattice); everything else takes the one-tile kernel.
+// ------------------------------------------------------------------------------------------
+constexpr int TH2 = 2 * TH;
+
+// Reject masks of word J of BOTH thread ids of a thread (tc0: row ty, tc1: row ty + 16): the table values of a call
+// are fetched once for the two streams.
+template <int NTHR, int J>
+__device__ __forceinline__ void word_reject_masks2(const ThreadConsts& tc0, const ThreadConsts& tc1, const StepTables& st,
+                                                   uint32_t thrA, uint32_t thrB, uint32_t (&rejA)[2], uint32_t (&rejB)[2])
+{
+    uint32_t a0 = 0, b0 = 0, a1 = 0, b1 = 0;
+#pragma unroll
+    for (int q = 0; q < 8; q++) {
+        const int cl = 8 * J + q;
+        uint32_t o[4], u[4];
+        philox_fast(tc0, st.a[cl], st.b[cl], st.d[cl], st.k0, st.k1, o);
+        philox_fast(tc1, st.a[cl], st.b[cl], st.d[cl], st.k0, st.k1, u);
+        or_bit_if_gt(a0, o[0], thrA, 2 * q);
+        or_bit_if_gt(a0, o[1], thrA, 16 + 2 * q);
+        or_bit_if_gt(a0, o[2], thrA, 2 * q + 1);
+        or_bit_if_gt(a0, o[3], thrA, 17 + 2 * q);
+        or_bit_if_gt(a1, u[0], thrA, 2 * q);
+        or_bit_if_gt(a1, u[1], thrA, 16 + 2 * q);
+        or_bit_if_gt(a1, u[2], thrA, 2 * q + 1);
+        or_bit_if_gt(a1, u[3], thrA, 17 + 2 * q);
+        if (NTHR > 1) {
+            or_bit_if_gt(b0, o[0], thrB, 2 * q);
+            or_bit_if_gt(b0, o[1], thrB, 16 + 2 * q);
+            or_bit_if_gt(b0, o[2], thrB, 2 * q + 1);
+            or_bit_if_gt(b0, o[3], thrB, 17 + 2 * q);
+            or_bit_if_gt(b1, u[0], thrB, 2 * q);
+            or_bit_if_gt(b1, u[1], thrB, 16 + 2 * q);
+            or_bit_if_gt(b1, u[2], thrB, 2 * q + 1);
+            or_bit_if_gt(b1, u[3], thrB, 17 + 2 * q);
+        }
+    }
+    rejA[0] = a0; rejA[1] = a1;
+    rejB[0] = b0; rejB[1] = b1;
+}
+
+template <bool FAST>
+__global__ void __launch_bounds__(UPDATE_THREADS, ISING_MIN_BLOCKS)
+update_color_kernel2(const __grid_constant__ CUtensorMap src_tile2 /* box 32 x 32 */,
+                     const __grid_constant__ CUtensorMap src_row /* box 32 x 1 */,
+                     const __grid_constant__ CUtensorMap src_side2 /* box 4 x 32 */, uint32_t* __restrict__ dst /* local row 0 */,
+                     const __grid_constant__ UpdateParams p)
+{
+    __shared__ alignas(128) uint32_t sV[(TH2 + 2) * TW];   // rows: above, 32 centre rows, below
+    __shared__ alignas(128) uint32_t sL[TH2 * SIDE_W];
+    __shared__ alignas(128) uint32_t sR[TH2 * SIDE_W];
+    __shared__ alignas(8) uint64_t bar;
+
+    const int by = (int)(blockIdx.z * gridDim.y + blockIdx.y);   // 32-row unit of this launch
+    if (by >= p.launch_tile_rows) return;
+    const int x0 = blockIdx.x * TW;                     // first word of the tile in the row
+    const int y0 = p.tile_row0 * TH + by * TH2;         // first local row of the tile (tile_row0 counts 16-row units)
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+
+    uint32_t* const my = dst + (size_t)(y0 + ty) * p.pitch + x0 + tx;
+    const size_t lower = (size_t)TH * p.pitch;          // same column, 16 rows down
+    uint32_t me[2][2];                                  // [row ty / ty + 16][word tx / tx + 16]
+
+    if (threadIdx.x < 32) {                             // see update_color_kernel: no CTA-wide barrier
+        if (threadIdx.x == 0) {
+            mbar_init(&bar, 1);
+            fence_mbar_init();
+        }
+        __threadfence_block();
+        __syncwarp();
+#pragma unroll
+        for (int w = 1; w < UPDATE_THREADS / 32; w++) asm volatile("barrier.cta.arrive %0, 64;" ::"r"(w) : "memory");
+    }
+    me[0][0] = my[0];
+    me[0][1] = my[16];
+    me[1][0] = my[lower];
+    me[1][1] = my[lower + 16];
+    if (threadIdx.x < 32) {
+        // the four wrap tests on four lanes: one division for the warp
+        const int lane = threadIdx.x;
+        unsigned int n = 0, d = 1;
+        if (lane == 0) { n = (unsigned)x0; d = (unsigned)p.xperiod; }
+        if (lane == 1) { n = (unsigned)(x0 + TW); d = (unsigned)p.xperiod; }
+        if (p.yperiod > 0) {
+            if (lane == 2) { n = (unsigned)y0; d = (unsigned)p.yperiod; }
+            if (lane == 3) { n = (unsigned)(y0 + TH2); d = (unsigned)p.yperiod; }
+        }
+        const unsigned int wrap = __ballot_sync(0xffffffffu, (n % d) == 0u);
+        if (lane == 0) {
+            int ytop = y0 - 1, ybot = y0 + TH2;         // ghost rows when yperiod == 0
+            if (p.yperiod > 0) {
+                if (wrap & 4u) ytop = y0 + p.yperiod - 1;
+                if (wrap & 8u) ybot = y0 + TH2 - p.yperiod;
+            }
+            const int xl = (wrap & 1u) ? x0 + p.xperiod - 1 : x0 - 1;
+            const int xr = (wrap & 2u) ? x0 + TW - p.xperiod : x0 + TW;
+            constexpr uint32_t bytes = ((TH2 + 2) * TW + 2 * TH2 * SIDE_W) * 4;
+            mbar_expect_tx(&bar, bytes);
+            // allocation row = local row + 1 (row 0 of the allocation is the upper ghost row)
+            tma_load_2d(sV + TW, &src_tile2, x0, y0 + 1, &bar);
+            tma_load_2d(sV, &src_row, x0, ytop + 1, &bar);
+            tma_load_2d(sV + (TH2 + 1) * TW, &src_row, x0, ybot + 1, &bar);
+            tma_load_2d(sL, &src_side2, xl - (SIDE_W - 1), y0 + 1, &bar);
+            tma_load_2d(sR, &src_side2, xr, y0 + 1, &bar);
+        }
+    }
+
+    const uint32_t grow = p.grow0 + (uint32_t)(y0 + ty);
+    const uint32_t tid0 = ref_tid(grow, (uint32_t)(x0 + tx), p.grid_x);
+    const uint32_t tid1 = tid0 + p.grid_x * 256u;       // 16 rows down = the next block row of the reference grid
+    const ThreadConsts tc0 = make_thread_consts(tid0, p.st.x1, p.st.k1r3);
+    const ThreadConsts tc1 = make_thread_consts(tid1, p.st.x1, p.st.k1r3);
+    // side neighbour is at colour-column m-1 ("readBack", main.cu:542) or m+1; rows ty and ty + 16 have one parity
+    const bool read_back = (p.color == 0) ? !(grow & 1u) : (grow & 1u);
+
+    uint32_t rejA[2][2], rejB[2][2];                    // [word][row]
+    if (FAST || p.rule.selB[0] | p.rule.selB[1] | p.rule.selB[2] | p.rule.selB[3] | p.rule.selB[4]) {
+        word_reject_masks2<2, 0>(tc0, tc1, p.st, p.rule.thrA, p.rule.thrB, rejA[0], rejB[0]);
+        word_reject_masks2<2, 1>(tc0, tc1, p.st, p.rule.thrA, p.rule.thrB, rejA[1], rejB[1]);
+    } else {
+        word_reject_masks2<1, 0>(tc0, tc1, p.st, p.rule.thrA, p.rule.thrB, rejA[0], rejB[0]);
+        word_reject_masks2<1, 1>(tc0, tc1, p.st, p.rule.thrA, p.rule.thrB, rejA[1], rejB[1]);
+    }
+
+    if (threadIdx.x >= 32) asm volatile("barrier.cta.sync %0, 64;" ::"r"((int)(threadIdx.x >> 5)) : "memory");
+    mbar_wait(&bar, 0);
+
+#pragma unroll
+    for (int t = 0; t < 2; t++) {
+        const int r = ty + TH * t;                      // row inside the 32-row tile
+#pragma unroll
+        for (int j = 0; j < 2; j++) {
+            const int w = tx + 16 * j;
+            const uint32_t up = sV[r * TW + w];
+            const uint32_t ct = sV[(r + 1) * TW + w];
+            const uint32_t dn = sV[(r + 2) * TW + w];
+            uint32_t sd;
+            if (read_back) {
+                const uint32_t prev = (w == 0) ? sL[r * SIDE_W + SIDE_W - 1] : sV[(r + 1) * TW + w - 1];
+                sd = __funnelshift_l(prev, ct, 1);    // (ct << 1) | (prev >> 31)
+            } else {
+                const uint32_t next = (w == TW - 1) ? sR[r * SIDE_W] : sV[(r + 1) * TW + w + 1];
+                sd = __funnelshift_r(ct, next, 1);    // (ct >> 1) | (next << 31)
+            }
+            me[t][j] ^= flip_mask<FAST>(me[t][j], up, dn, ct, sd, rejA[j][t], rejB[j][t], p.rule);
+            my[t * lower + 16 * j] = me[t][j];
+        }
     }
 }
 
@@ -590,10 +762,18 @@ void launch_update(const CUtensorMap& src_tile, const CUtensorMap& src_row, cons
 #undef ISING_LAUNCH
 }
 
+void launch_update2(const CUtensorMap& src_tile2, const CUtensorMap& src_row, const CUtensorMap& src_side2, uint32_t* dst,
+                    const UpdateParams& p, int tiles_x, int tile_rows32, cudaStream_t stream)
+{
+    const dim3 grid = tile_grid(tiles_x, tile_rows32);
+    if (p.rule.fast) update_color_kernel2<true><<<grid, UPDATE_THREADS, 0, stream>>>(src_tile2, src_row, src_side2, dst, p);
+    else             update_color_kernel2<false><<<grid, UPDATE_THREADS, 0, stream>>>(src_tile2, src_row, src_side2, dst, p);
+}
+
 const char* update_kernel_name(int fast)
 {
-    return fast ? "update_color_kernel<fast: 2 integer thresholds, TMA 16x32-word tiles, 1 bit/spin>"
-                : "update_color_kernel<generic acceptance rule, TMA 16x32-word tiles, 1 bit/spin>";
+    return fast ? "update_color_kernel2<fast: 2 integer thresholds, TMA 32x32-word tiles, 2 Philox streams per thread, 1 bit/spin>"
+                : "update_color_kernel2<generic acceptance rule, TMA 32x32-word tiles, 2 Philox streams per thread, 1 bit/spin>";
 }
 
 // ------------------------------------------------------------------------------------------

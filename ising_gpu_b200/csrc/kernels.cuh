@@ -99,6 +99,10 @@ struct CorrParams {
 void launch_update(const CUtensorMap& src_tile, const CUtensorMap& src_row, const CUtensorMap& src_side,
                    uint32_t* dst_local_row0, const uint32_t* bond_planes, const UpdateParams& p, int tiles_x,
                    int tiles_y, cudaStream_t stream);
+// two stacked tiles per CTA (32 rows), two reference thread ids per thread; tile_row0 of p in 16-row units,
+// tile_rows32 = number of 32-row units covered; no bonds, no fused push
+void launch_update2(const CUtensorMap& src_tile2, const CUtensorMap& src_row, const CUtensorMap& src_side2,
+                    uint32_t* dst_local_row0, const UpdateParams& p, int tiles_x, int tile_rows32, cudaStream_t stream);
 void launch_bond_init(uint32_t* random_planes_alloc_row0, uint32_t* mirror_planes_local_row0, const BondParams& p,
                       cudaStream_t stream);
 void launch_corr(const CorrParams& p, unsigned long long* equal_counts, cudaStream_t stream);
