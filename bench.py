@@ -65,6 +65,8 @@ README_KAT = {
                                                    80: 2147558546, 96: 2147471275, 112: 2147612509, 128: 2147678887}),
     (2, 65536): ("optimized/README.md:240-249", {16: 4294617248, 32: 4293898346, 48: 4292806461, 64: 4291852263,
                                                    80: 4291086016, 96: 4290256223, 112: 4289621029, 128: 4288877118}),
+    (8, 65536): ("optimized/README.md:307-316", {16: 17176389528, 32: 17172963073, 48: 17170610910, 64: 17168843228,
+                                                   80: 17167009008, 96: 17165014291, 112: 17163708078, 128: 17162287230}),
 }
 DEFAULT_SEED = 463463564571
 
@@ -272,7 +274,7 @@ def run_b200(a):
     numa = None
     if world > 1:
         from ising_gpu_b200.slab import bind_process_near_gpu
-        numa = bind_process_near_gpu(local)     # host staging buffers next to the GPU's PCIe root
+        numa = bind_process_near_gpu(local, report=True)     # host staging buffers next to the GPU's PCIe root
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     rows = a.rows_per_gpu or default_rows(world)
     S = a.sweeps_per_step
@@ -348,7 +350,11 @@ def run_b200(a):
         ksteps = max(1, min(a.steps, a.e2e_steps)) if a.e2e_steps else a.steps
         flips_e2e = float(X_COLS) * rows * S * ksteps * world
 
-        def pinned():
+        def pinned(wc=False):
+            if wc:      # write-combined input staging (ising_host_alloc): the host only ever writes these
+                from ising_gpu_b200.engine import HostBuffer
+                hb = HostBuffer((rows, pitch), write_combined=True)
+                return hb, hb.array
             t = torch.empty((rows, pitch), dtype=torch.int32).pin_memory()
             return t, t.numpy().view(np.uint32)
 
@@ -381,12 +387,12 @@ def run_b200(a):
         ready = True
         try:        # pinned host memory is the one local resource that can run out here
             for j in range(2):
-                (tb, nb), (tw, nw) = pinned(), pinned()
+                (tb, nb), (tw, nw) = pinned(a.staging == "wc"), pinned(a.staging == "wc")
                 nb[:], nw[:] = b0, w0
                 (tob, nob), (tow, now) = pinned(), pinned()
                 keep += [tb, tw, tob, tow]
                 ins.append((nb, nw)); outs.append((nob, now))
-        except RuntimeError:
+        except (RuntimeError, Exception):
             ready = False
         ready = bool(-allmax(-float(ready))[0])           # every rank enters the batch, or none does
         runs_dl, runs = [], []
@@ -467,9 +473,9 @@ def run_b200(a):
             if not ok:
                 raise SystemExit("e2e: pipelined replica batch does not reproduce the unpipelined result")
         # dependent chain on one of the input buffers (always measured; the only e2e number without a batch)
-        if ins:
-            ins[0][0][:], ins[0][1][:] = b0, w0
-            cb, cw = ins[0]
+        if outs:     # (plain page-locked buffers: the chain downloads into what it uploads next)
+            outs[0][0][:], outs[0][1][:] = b0, w0
+            cb, cw = outs[0]
         else:
             (tb, cb), (tw, cw) = pinned(), pinned()
             cb[:], cw[:] = b0, w0
@@ -485,7 +491,7 @@ def run_b200(a):
                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 8 * world, "steps": ksteps,
                    "timer": "host monotonic clock around the synchronised region, max over ranks; two runs of %d steps, "
                             "the better one is `value`" % ksteps,
-                   "runs": [round(flips_e2e / (x * 1e9), 2) for x in runs], "api": api, "numa_node_of_rank0": numa,
+                   "runs": [round(flips_e2e / (x * 1e9), 2) for x in runs], "api": api, "numa_of_rank0": numa, "input_staging": a.staging,
                    "with_lattice_download": {"value": round(flips_e2e / (min(runs_dl) * 1e9), 2), "unit": "flips/ns",
                                              "runs": [round(flips_e2e / (x * 1e9), 2) for x in runs_dl],
                                              "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": (2 * plane_bytes + 8) * world},
@@ -493,7 +499,7 @@ def run_b200(a):
         else:
             e2e = dict(chain)
             e2e.update({"steps": ksteps, "timer": "host monotonic clock around the synchronised region, max over ranks",
-                        "numa_node_of_rank0": numa, "dependent_chain": chain,
+                        "numa_of_rank0": numa, "dependent_chain": chain,
                         "note": "no replica batch on this transport (halo=%s%s)" % (a.halo, "" if ready else
                                                                                    ", pinned host memory exhausted")})
 
@@ -666,6 +672,8 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=0, help="steps of the e2e leg (0 = --steps)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--staging", default="pinned", choices=["pinned", "wc"],
+                    help="e2e input buffers: plain page-locked memory, or write-combined (ising_host_alloc)")
     ap.add_argument("--no-tc", action="store_true", help="skip the tensor-core variant leg (variants.tensorcore)")
     ap.add_argument("--no-selfcheck", action="store_true", help="N > 1: skip the small slab-vs-1-GPU comparison")
     ap.add_argument("--no-overlap", action="store_true")

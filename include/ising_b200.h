@@ -189,6 +189,12 @@ int ising_run_slab_batch_from_host(ising_ctx* ctx_a, ising_ctx* ctx_b, int nrep,
                                    const uint32_t* const* white_in, const uint32_t* const* ghosts_in, int first_it, int n,
                                    uint32_t* const* black_out, uint32_t* const* white_out, uint64_t* up, uint64_t* down);
 
+/* Page-locked host staging memory for the *_from_host calls (cudaHostAlloc, portable).  write_combined != 0 asks for
+ * write-combined memory: faster for the device to read over PCIe and it does not pollute the CPU caches, but slow for
+ * the CPU to read -- use it for buffers the host only writes (inputs), never for outputs. */
+int ising_host_alloc(size_t bytes, int write_combined, void** ptr);
+int ising_host_free(void* ptr);
+
 /* ---- multi-process slabs (one process per GPU) ------------------------------------------
  * Device pointer and byte length of one row of a colour plane.  row = -1 is the ghost row
  * above the slab, row = Y the ghost row below it, 0..Y-1 the slab's own rows.  The caller

@@ -1128,6 +1128,22 @@ int ising_run_slab_batch_from_host(ising_ctx* ctx_a, ising_ctx* ctx_b, int nrep,
     return run_batch(ctx_a, ctx_b, nrep, black_in, white_in, ghosts_in, first_it, n, black_out, white_out, up, down);
 }
 
+int ising_host_alloc(size_t bytes, int write_combined, void** ptr)
+{
+    if (!ptr || !bytes) return fail(ISING_EINVAL, "bad argument");
+    *ptr = nullptr;
+    const unsigned int flags = cudaHostAllocPortable | (write_combined ? cudaHostAllocWriteCombined : 0u);
+    const cudaError_t e = cudaHostAlloc(ptr, bytes, flags);
+    if (e != cudaSuccess) return fail(ISING_ENOMEM, "cudaHostAlloc(%zu): %s", bytes, cudaGetErrorString(e));
+    return ISING_OK;
+}
+
+int ising_host_free(void* ptr)
+{
+    if (ptr) CU_TRY(cudaFreeHost(ptr));
+    return ISING_OK;
+}
+
 int ising_row_ptr(ising_ctx* c, int dev, int color, int row, void** dptr, size_t* nbytes)
 {
     if (int rc = check_dev(c, dev)) return rc;

@@ -81,6 +81,8 @@ def load_library():
                                             C.POINTER(vp), C.POINTER(vp), u64p, u64p], C.c_int),
         "ising_row_ptr": ([vp, C.c_int, C.c_int, C.c_int, C.POINTER(vp), C.POINTER(C.c_size_t)], C.c_int),
         "ising_update_color_part": ([vp, C.c_int, C.c_int, C.c_int, C.c_int, vp], C.c_int),
+        "ising_host_alloc": ([C.c_size_t, C.c_int, C.POINTER(vp)], C.c_int),
+        "ising_host_free": ([vp], C.c_int),
         "ising_device_count": ([C.POINTER(C.c_int)], C.c_int),
         "ising_device_info": ([C.c_int, C.c_char_p, C.c_size_t] + [C.POINTER(C.c_int)] * 5, C.c_int),
         "ising_can_access_peer": ([C.c_int, C.c_int, C.POINTER(C.c_int)], C.c_int),
@@ -122,7 +124,7 @@ EXPORTED_SYMBOLS = ("ising_create ising_destroy ising_last_error ising_abi_versi
                     "ising_export_bonds_ref_layout ising_export_ref_layout "
                     "ising_import_ref_layout ising_export_bits ising_import_bits ising_dump_lattice "
                     "ising_save_checkpoint ising_load_checkpoint "
-                    "ising_run_from_host ising_run_batch_from_host ising_run_slab_batch_from_host ising_row_ptr ising_update_color_part ising_accept_count "
+                    "ising_run_from_host ising_run_batch_from_host ising_run_slab_batch_from_host ising_row_ptr ising_update_color_part ising_host_alloc ising_host_free ising_accept_count "
                     "ising_device_count ising_device_info ising_can_access_peer "
                     "ising_ipc_export ising_ipc_attach ising_push_edges "
                     "ising_accept_table ising_site_random ising_launch_count ising_kernel_name "
@@ -130,6 +132,33 @@ EXPORTED_SYMBOLS = ("ising_create ising_destroy ising_last_error ising_abi_versi
                     "ising_tc_update_timed ising_tc_sync ising_tc_sum ising_tc_export_storage "
                     "ising_tc_import_storage ising_tc_export_true ising_tc_write_lattice ising_tc_accept_table "
                     "ising_tc_neighbour_sums ising_tc_launch_count").split()
+
+
+class HostBuffer:
+    """Page-locked staging buffer from ising_host_alloc as a numpy uint32 array (`.array`); write_combined buffers are
+    for inputs only (the CPU should never read them)."""
+
+    def __init__(self, shape, write_combined=False):
+        self._L = load_library()
+        n = int(np.prod(shape)) * 4
+        p = C.c_void_p()
+        rc = self._L.ising_host_alloc(n, int(bool(write_combined)), C.byref(p))
+        if rc != 0:
+            raise IsingError(rc, self._L.ising_last_error().decode())
+        self._p = p
+        self.array = np.ctypeslib.as_array((C.c_uint32 * (n // 4)).from_address(p.value)).reshape(shape)
+
+    def close(self):
+        if getattr(self, "_p", None):
+            self.array = None
+            self._L.ising_host_free(self._p)
+            self._p = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def accept_count(p, strict=False):

@@ -19,29 +19,90 @@ import torch.distributed as dist
 from .engine import F_NO_PEER_COPY, PART_ALL, PART_EDGES, PART_INTERIOR, IsingEngine
 
 
-def bind_process_near_gpu(device):
-    """Pin this process (and the pinned host memory it allocates from now on) to the NUMA node the GPU hangs
-    off: with one process per GPU and no binding, the staging buffers of half the ranks end up on the other
-    socket and every H2D/D2H crosses the inter-socket link.  Returns the node, or None when it cannot be
-    determined (no sysfs entry, a single node, no permission) -- then nothing is changed."""
+def _cpulist(text):
+    cpus = set()
+    for part in text.strip().split(","):
+        if not part:
+            continue
+        lo, _, hi = part.partition("-")
+        cpus.update(range(int(lo), int(hi or lo) + 1))
+    return cpus
+
+
+def parse_nvidia_smi_topo(text, gpu):
+    """(cpus, numa_node or None) of physical GPU `gpu` from the matrix `nvidia-smi topo -m` prints: tab-separated,
+    one row per GPU, the columns "CPU Affinity" and "NUMA Affinity" after the link matrix."""
+    import re
+    lines = [re.sub(r"\x1b\[[0-9;]*m", "", ln) for ln in text.splitlines() if ln.strip()]
+    hdr = next((ln for ln in lines if "CPU Affinity" in ln), None)
+    row = next((ln for ln in lines if re.match(r"GPU%d\s" % gpu, ln)), None)
+    if hdr is None or row is None:
+        return set(), None
+    cols = [c.strip() for c in hdr.split("\t")]
+    cells = [c.strip() for c in row.split("\t")]
+    if cols and cols[0] != "":          # no (empty) header cell above the row labels: shift
+        cols = [""] + cols
+    def cell(name):
+        return cells[cols.index(name)] if name in cols and cols.index(name) < len(cells) else ""
+    try:
+        cpus = _cpulist(cell("CPU Affinity"))
+    except ValueError:
+        cpus = set()
+    n = cell("NUMA Affinity")
+    node = int(re.split(r"[,-]", n)[0]) if n[:1].isdigit() else None
+    return cpus, node
+
+
+def gpu_numa_topology(device):
+    """Where the GPU hangs in the host: {"nodes": NUMA nodes of the box, "gpu_node": node of the GPU or None,
+    "cpus": CPUs next to it, "source": where that came from}.  sysfs first (numa_node of the PCI function); when
+    the platform reports -1 there, the "CPU Affinity" / "NUMA Affinity" columns of `nvidia-smi topo -m`."""
+    import glob
     import os
+    import subprocess
+    info = {"nodes": len(glob.glob("/sys/devices/system/node/node[0-9]*")), "gpu_node": None, "cpus": set(), "source": None}
     try:
         pr = torch.cuda.get_device_properties(device)
         bdf = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
         node = int(open("/sys/bus/pci/devices/%s/numa_node" % bdf).read().strip())
-        if node < 0:
-            return None
-        cpus = set()
-        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
-            lo, _, hi = part.partition("-")
-            cpus.update(range(int(lo), int(hi or lo) + 1))
-        cpus &= os.sched_getaffinity(0)
-        if not cpus:
-            return None
-        os.sched_setaffinity(0, cpus)
-        return node
+        if node >= 0:
+            info.update(gpu_node=node, source="sysfs",
+                        cpus=_cpulist(open("/sys/devices/system/node/node%d/cpulist" % node).read()))
+            return info
     except Exception:
-        return None
+        pass
+    try:
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        phys = int(vis.split(",")[device]) if vis and all(x.strip().isdigit() for x in vis.split(",")) else device
+        out = subprocess.run(["nvidia-smi", "topo", "-m"], capture_output=True, text=True, timeout=20).stdout
+        cpus, node = parse_nvidia_smi_topo(out, phys)
+        if cpus:
+            info.update(gpu_node=node, cpus=cpus, source="nvidia-smi topo")
+    except Exception:
+        pass
+    return info
+
+
+def bind_process_near_gpu(device, report=False):
+    """Pin this process (and the pinned host memory it allocates from now on: first touch) to the CPUs next to the
+    GPU: with one process per GPU and no binding, the staging buffers of half the ranks end up on the other socket
+    and every H2D/D2H crosses the inter-socket link.  Returns the NUMA node, or None when it cannot be determined or
+    there is nothing to choose (a single node, no permission) -- then nothing is changed.  report=True returns the
+    whole finding as a dict instead."""
+    import os
+    info = gpu_numa_topology(device)
+    bound = False
+    try:
+        cpus = info["cpus"] & os.sched_getaffinity(0)
+        if cpus and info["nodes"] != 1 and cpus != os.sched_getaffinity(0):
+            os.sched_setaffinity(0, cpus)
+            bound = True
+    except Exception:
+        pass
+    if report:
+        return {"nodes": info["nodes"], "gpu_node": info["gpu_node"], "source": info["source"], "bound": bound,
+                "cpus_near_gpu": len(info["cpus"]), "cpus_allowed": len(os.sched_getaffinity(0))}
+    return info["gpu_node"] if bound else None
 
 
 class HaloExchange:

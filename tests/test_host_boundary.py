@@ -112,3 +112,16 @@ def test_shipped_kernels_are_blackwell_native():
     assert hs["update_color_kernel_fast"]["ops"]["UTMALDG"] == 5
     # no mma.sync / wgmma fallbacks anywhere in the variant kernel
     assert not any(k.startswith(("HMMA", "IMMA")) for k in hs["tc_update_pipe_kernel"]["ops"])
+
+
+def test_nvidia_smi_topo_parser():
+    """The fallback of the NUMA helper when sysfs reports no node for the GPU."""
+    from ising_gpu_b200.slab import parse_nvidia_smi_topo
+    txt = ("\tGPU0\tGPU1\tNIC0\tCPU Affinity\tNUMA Affinity\tGPU NUMA ID\n"
+           "GPU0\t X \tNV18\tSYS\t0-3,64-67\t0\t\tN/A\n"
+           "GPU1\tNV18\t X \tSYS\t32-35\t1\t\tN/A\n"
+           "NIC0\tSYS\tSYS\t X \t\t\t\t\n\nLegend:\n  X    = Self\n")
+    assert parse_nvidia_smi_topo(txt, 0) == ({0, 1, 2, 3, 64, 65, 66, 67}, 0)
+    assert parse_nvidia_smi_topo(txt, 1) == ({32, 33, 34, 35}, 1)
+    assert parse_nvidia_smi_topo(txt, 5) == (set(), None)
+    assert parse_nvidia_smi_topo("garbage", 0) == (set(), None)

@@ -13,6 +13,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "ising_gpu_b200", "libising_b200.so")
 # kernel tag -> regex on the mangled name
 KERNELS = {
+    "update_color_kernel2_fast": r"update_color_kernel2ILb1E",
     "update_color_kernel_fast": r"update_color_kernelILb1ELb0ELb0E",
     "update_color_kernel_fast_push": r"update_color_kernelILb1ELb0ELb1E",
     "update_color_persistent_fast": r"update_color_persistentILb1ELb0ELb0E",
@@ -20,7 +21,8 @@ KERNELS = {
     "init_kernel": r"init_kernel",
     "count_kernel": r"count_kernel",
 }
-MUST = {"update_color_kernel_fast": ["UTMALDG", "SYNCS", "IMAD.WIDE.U32"],
+MUST = {"update_color_kernel2_fast": ["UTMALDG", "SYNCS", "IMAD.WIDE.U32"],
+        "update_color_kernel_fast": ["UTMALDG", "SYNCS", "IMAD.WIDE.U32"],
         "update_color_persistent_fast": ["UTMALDG", "SYNCS", "IMAD.WIDE.U32"],
         "tc_update_pipe_kernel": ["UTCIMMA", "LDTM", "UTMALDG", "SYNCS"]}
 
