@@ -68,40 +68,42 @@ def test_slabs_on_one_gpu_with_manual_halo(ig, oracle, nslab, Y):
         e.close()
 
 
-@pytest.mark.parametrize("mode", ["fused", "copy"])
-def test_single_process_two_devices(ig, oracle, mode, monkeypatch):
-    """cuIsing -d 2 path: one context, two GPUs; halo pushed by the kernel (default) or copied."""
-    if _ngpu() < 2:
-        pytest.skip("needs 2 GPUs")
+@pytest.mark.parametrize("ndev,mode", [(2, "fused"), (2, "copy"), (4, "fused"), (8, "fused"), (8, "copy")])
+def test_single_process_n_devices(ig, oracle, ndev, mode, monkeypatch):
+    """cuIsing -d N path: one context, N GPUs; halo pushed by the kernel (default) or copied.  Y = 96 rows per device
+    gives 6 tile rows: the edge launch on its own stream and the two-tiles-per-CTA interior both run."""
+    if _ngpu() < ndev:
+        pytest.skip("needs %d GPUs" % ndev)
     monkeypatch.setenv("ISING_B200_HALO", mode)
-    X, Y, sweeps = 4096, 64, 4
-    with ig.IsingEngine(X, Y, ndev=2, temp=TC) as eng:
+    X, Y, sweeps = 4096, 96, 4
+    with ig.IsingEngine(X, Y, ndev=ndev, temp=TC) as eng:
         eng.init_lattice()
         eng.sweeps(sweeps)
-        ob, ow, cnt = _oracle_planes(oracle, X, 2 * Y, sweeps, TC)
-        gb = np.vstack([eng.export_bits(d)[0] for d in range(2)])
-        gw = np.vstack([eng.export_bits(d)[1] for d in range(2)])
+        ob, ow, cnt = _oracle_planes(oracle, X, ndev * Y, sweeps, TC)
+        gb = np.vstack([eng.export_bits(d)[0] for d in range(ndev)])
+        gw = np.vstack([eng.export_bits(d)[1] for d in range(ndev)])
         assert np.array_equal(gb, ob) and np.array_equal(gw, ow)
         assert eng.count_spins() == cnt
+        assert abs(eng.energy_per_site() - (-2.0 * eng.correlation(1)[0])) < 1e-12   # ghost rows current on every device
 
 
-@pytest.mark.parametrize("overlap", [1, 0, 2])
-def test_one_process_per_gpu_nccl(oracle, tmp_path, overlap):
-    """torchrun, 2 ranks; halo over NCCL (1 overlapped, 0 serialised) or pushed by the update kernel
+@pytest.mark.parametrize("nranks,overlap", [(2, 1), (2, 0), (2, 2), (4, 2), (8, 2), (8, 1)])
+def test_one_process_per_gpu_nccl(oracle, tmp_path, nranks, overlap):
+    """torchrun, N ranks; halo over NCCL (1 overlapped, 0 serialised) or pushed by the update kernel
     itself through CUDA-IPC peer memory (2): stacked slabs == oracle."""
-    if _ngpu() < 2:
-        pytest.skip("needs 2 GPUs")
-    X, Y, sweeps = 4096, 64, 5
+    if _ngpu() < nranks:
+        pytest.skip("needs %d GPUs" % nranks)
+    X, Y, sweeps = 4096, 96, 5
     out = tmp_path / "slabs"
     out.mkdir()
-    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr",
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=%d" % nranks, "--master-addr",
            "127.0.0.1", "--master-port", "29533", os.path.join(ROOT, "tests", "slab_worker.py"), str(X), str(Y),
            str(sweeps), str(TC), str(overlap), str(out)]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
-    ob, ow, cnt = _oracle_planes(oracle, X, 2 * Y, sweeps, TC)
-    gb = np.vstack([np.load(out / ("b%d.npy" % k)) for k in range(2)])
-    gw = np.vstack([np.load(out / ("w%d.npy" % k)) for k in range(2)])
+    ob, ow, cnt = _oracle_planes(oracle, X, nranks * Y, sweeps, TC)
+    gb = np.vstack([np.load(out / ("b%d.npy" % k)) for k in range(nranks)])
+    gw = np.vstack([np.load(out / ("w%d.npy" % k)) for k in range(nranks)])
     assert np.array_equal(gb, ob) and np.array_equal(gw, ow)
 
 
