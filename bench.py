@@ -384,14 +384,18 @@ def run_b200(a):
             return time.perf_counter() - t0
 
         keep, ins, outs = [], [], []
+        NCTX = max(1, a.e2e_contexts)   # contexts per GPU the jobs rotate over
         ready = True
         try:        # pinned host memory is the one local resource that can run out here
-            for j in range(2):
+            for j in range(2):          # inputs: two lattices, uploaded alternately
                 (tb, nb), (tw, nw) = pinned(a.staging == "wc"), pinned(a.staging == "wc")
                 nb[:], nw[:] = b0, w0
+                keep += [tb, tw]
+                ins.append((nb, nw))
+            for j in range(NCTX):       # outputs: one landing zone per context in flight
                 (tob, nob), (tow, now) = pinned(), pinned()
-                keep += [tb, tw, tob, tow]
-                ins.append((nb, nw)); outs.append((nob, now))
+                keep += [tob, tow]
+                outs.append((nob, now))
         except (RuntimeError, Exception):
             ready = False
         ready = bool(-allmax(-float(ready))[0])           # every rank enters the batch, or none does
@@ -403,24 +407,26 @@ def run_b200(a):
             # pinned memory, S sweeps, spin counts, download both planes; jobs alternate between two
             # contexts so the copies of one step overlap the kernels of the next (ising_run_batch_from_host)
             from ising_gpu_b200.engine import IsingEngine
-            eng2 = IsingEngine(X_COLS, rows, seed=a.seed, temp=TEMP, first_device=local)
+            others = [IsingEngine(X_COLS, rows, seed=a.seed, temp=TEMP, first_device=local) for _ in range(NCTX - 1)]
 
             def batch(k, download):
-                return eng.eng.run_batch_from_host(eng2, [ins[j & 1][0] for j in range(k)],
+                return eng.eng.run_batch_from_host(others, [ins[j & 1][0] for j in range(k)],
                                                    [ins[j & 1][1] for j in range(k)], S,
-                                                   [outs[j & 1][0] for j in range(k)] if download else None,
-                                                   [outs[j & 1][1] for j in range(k)] if download else None,
+                                                   [outs[j % NCTX][0] for j in range(k)] if download else None,
+                                                   [outs[j % NCTX][1] for j in range(k)] if download else None,
                                                    first_it=eng.it + 1)
             want_counts = None
-            api = ("ising_run_batch_from_host (C ABI, pinned host buffers): per step H2D of both planes, %d sweeps, "
-                   "count kernels, D2H of the spin counts; two contexts, copies overlap the other step's kernels" % S)
+            api = ("ising_run_batch_from_host_n (C ABI, pinned host buffers): per step H2D of both planes, %d sweeps, "
+                   "count kernels, D2H of the spin counts; %d contexts, copies overlap the other steps' kernels" % (S, NCTX))
         elif ready and a.halo == "fused":
             # the same replica batch on every rank's slab (ising_run_slab_batch_from_host): per step H2D of the
             # slab's planes and white ghost rows, S sweeps with the fused halo push between the ranks, counts,
             # D2H of the planes; two contexts per rank so that copies overlap the other step's kernels
-            with torch.cuda.stream(torch.cuda.Stream()):   # SlabEngine works on the stream current at construction
-                eng2 = SlabEngine(X_COLS, rows, TEMP, a.seed, rank=rank, world=world, device=local, halo="fused")
-            eng2.init_lattice()
+            others = []
+            for _ in range(NCTX - 1):
+                with torch.cuda.stream(torch.cuda.Stream()):   # SlabEngine works on the stream current at construction
+                    others.append(SlabEngine(X_COLS, rows, TEMP, a.seed, rank=rank, world=world, device=local, halo="fused"))
+                others[-1].init_lattice()
             # one unpipelined step first: gives the ghost rows that belong to the uploaded state and the
             # result the pipelined steps must reproduce
             it0 = eng.it
@@ -430,25 +436,27 @@ def run_b200(a):
             eng.sweeps(S)
             want_b, want_w = eng.eng.export_bits()
             want_counts = eng.count_spins()
-            eng.it = eng2.it = it0
+            eng.it = it0
+            for o in others:
+                o.it = it0
             tg = torch.empty((2, pitch), dtype=torch.int32).pin_memory()
             ng = tg.numpy().view(np.uint32)
             ng[:] = ghosts
 
             def batch(k, download):
-                return eng.run_batch_from_host(eng2, [ins[j & 1][0] for j in range(k)],
+                return eng.run_batch_from_host(others, [ins[j & 1][0] for j in range(k)],
                                                [ins[j & 1][1] for j in range(k)], [ng] * k, S,
-                                               [outs[j & 1][0] for j in range(k)] if download else None,
-                                               [outs[j & 1][1] for j in range(k)] if download else None)
-            api = ("ising_run_slab_batch_from_host (C ABI, pinned host buffers): per step and rank H2D of the slab's planes "
+                                               [outs[j % NCTX][0] for j in range(k)] if download else None,
+                                               [outs[j % NCTX][1] for j in range(k)] if download else None)
+            api = ("ising_run_batch_from_host_n (C ABI, pinned host buffers): per step and rank H2D of the slab's planes "
                    "and white ghost rows, %d sweeps with the fused halo push, count kernels, D2H of the spin counts; "
-                   "two contexts per rank, copies overlap the other step's kernels; result checked against the "
-                   "unpipelined path" % S)
+                   "%d contexts per rank, copies overlap the other steps' kernels; result checked against the "
+                   "unpipelined path" % (S, NCTX))
         else:
             batch = None
         if batch is not None:
             def timed(download):
-                batch(2, download)
+                batch(NCTX, download)
                 out = []
                 for _ in range(2):                   # two runs of K steps, both reported; the better one is the value
                     barrier()                        # (the reference arm does the same)
@@ -460,16 +468,17 @@ def run_b200(a):
             runs_dl, counts = timed(True)            # D2H of the final planes as well (a checkpoint per step)
             if world == 1:
                 ok = (len(set(counts)) == 1 and counts[0][0] + counts[0][1] == X_COLS * rows and
-                      np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1]))
+                      all(np.array_equal(outs[0][0], o[0]) and np.array_equal(outs[0][1], o[1]) for o in outs[1:min(NCTX, ksteps)]))
             else:
                 ok = all(c == want_counts for c in counts) and all(
-                    np.array_equal(ob, want_b) and np.array_equal(ow, want_w) for ob, ow in outs[:min(2, ksteps)])
+                    np.array_equal(ob, want_b) and np.array_equal(ow, want_w) for ob, ow in outs[:min(NCTX, ksteps)])
             runs, counts2 = timed(False)             # D2H of the step's observable only
             ok = ok and counts2 == counts
             ok = bool(-allmax(-float(ok))[0])
             runs_dl = [allmax(x)[0] for x in runs_dl]
             runs = [allmax(x)[0] for x in runs]
-            eng2.close()
+            for o in others:
+                o.close()
             if not ok:
                 raise SystemExit("e2e: pipelined replica batch does not reproduce the unpipelined result")
         # dependent chain on one of the input buffers (always measured; the only e2e number without a batch)
@@ -491,7 +500,7 @@ def run_b200(a):
                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 8 * world, "steps": ksteps,
                    "timer": "host monotonic clock around the synchronised region, max over ranks; two runs of %d steps, "
                             "the better one is `value`" % ksteps,
-                   "runs": [round(flips_e2e / (x * 1e9), 2) for x in runs], "api": api, "numa_of_rank0": numa, "input_staging": a.staging,
+                   "runs": [round(flips_e2e / (x * 1e9), 2) for x in runs], "api": api, "numa_of_rank0": numa, "input_staging": a.staging, "contexts_per_gpu": NCTX,
                    "with_lattice_download": {"value": round(flips_e2e / (min(runs_dl) * 1e9), 2), "unit": "flips/ns",
                                              "runs": [round(flips_e2e / (x * 1e9), 2) for x in runs_dl],
                                              "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": (2 * plane_bytes + 8) * world},
@@ -672,6 +681,9 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=0, help="steps of the e2e leg (0 = --steps)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--e2e-contexts", type=int, default=3,
+                    help="contexts per GPU the e2e replica batch rotates over (2: a download and the next upload share "
+                         "one job's compute time; 3: they have two)")
     ap.add_argument("--staging", default="pinned", choices=["pinned", "wc"],
                     help="e2e input buffers: plain page-locked memory, or write-combined (ising_host_alloc)")
     ap.add_argument("--no-tc", action="store_true", help="skip the tensor-core variant leg (variants.tensorcore)")

@@ -188,6 +188,13 @@ int ising_run_batch_from_host(ising_ctx* ctx_a, ising_ctx* ctx_b, int nrep, cons
 int ising_run_slab_batch_from_host(ising_ctx* ctx_a, ising_ctx* ctx_b, int nrep, const uint32_t* const* black_in,
                                    const uint32_t* const* white_in, const uint32_t* const* ghosts_in, int first_it, int n,
                                    uint32_t* const* black_out, uint32_t* const* white_out, uint64_t* up, uint64_t* down);
+/* The same batches over nctx (1..8) contexts of one shape on one device, job k on ctxs[k % nctx].  With two contexts
+ * the download of job k and the upload of job k+2 share a stream and must BOTH fit into one job's compute time; with
+ * three they have two -- what it takes when many GPUs share the host's memory and PCIe fabric (8 GPUs: bench.py).
+ * ghosts_in NULL = single-slab contexts (ising_run_batch_from_host), else slab contexts with attached peers. */
+int ising_run_batch_from_host_n(ising_ctx* const* ctxs, int nctx, int nrep, const uint32_t* const* black_in,
+                                const uint32_t* const* white_in, const uint32_t* const* ghosts_in, int first_it, int n,
+                                uint32_t* const* black_out, uint32_t* const* white_out, uint64_t* up, uint64_t* down);
 
 /* Page-locked host staging memory for the *_from_host calls (cudaHostAlloc, portable).  write_combined != 0 asks for
  * write-combined memory: faster for the device to read over PCIe and it does not pollute the CPU caches, but slow for

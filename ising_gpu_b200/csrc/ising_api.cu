@@ -1031,12 +1031,15 @@ int ising_run_from_host(ising_ctx* c, const uint32_t* black_in, const uint32_t* 
 // one after the other at full speed while the upload of job k+1 and the download of job k-1 ride
 // on the copy engines -- without that the two streams run in lock-step and the SMs idle during
 // the copies.  A context is reused by job k+2 in stream order.
-static int run_batch(ising_ctx* ctx_a, ising_ctx* ctx_b, int nrep, const uint32_t* const* black_in,
+static int run_batch(ising_ctx* const* ctxs, int nctx, int nrep, const uint32_t* const* black_in,
                      const uint32_t* const* white_in, const uint32_t* const* ghosts_in, int first_it, int n,
                      uint32_t* const* black_out, uint32_t* const* white_out, uint64_t* up, uint64_t* down)
 {
-    ising_ctx* cs[2] = {ctx_a, ctx_b ? ctx_b : ctx_a};
-    if (!ctx_a || nrep < 0 || n < 0 || !black_in || !white_in) return fail(ISING_EINVAL, "bad argument");
+    if (!ctxs || nctx < 1 || nctx > 8 || !ctxs[0] || nrep < 0 || n < 0 || !black_in || !white_in)
+        return fail(ISING_EINVAL, "bad argument");
+    std::vector<ising_ctx*> cs;
+    for (int i = 0; i < nctx; i++) cs.push_back(ctxs[i] ? ctxs[i] : ctxs[0]);
+    ising_ctx* const ctx_a = cs[0];
     for (ising_ctx* c : cs) {
         if (c->dev.size() != 1) return fail(ISING_ESTATE, "replica batches need 1-device contexts");
         if (!ghosts_in && c->ghost_rows) return fail(ISING_ESTATE, "ising_run_batch_from_host needs 1-slab contexts");
@@ -1060,7 +1063,7 @@ static int run_batch(ising_ctx* ctx_a, ising_ctx* ctx_b, int nrep, const uint32_
     int rc = ISING_OK;
     cudaError_t e = cudaSuccess;
     for (int k = 0; k < nrep && rc == ISING_OK && e == cudaSuccess; k++) {
-        ising_ctx* c = cs[k & 1];
+        ising_ctx* c = cs[k % nctx];
         DevState& d = c->dev[0];
         if (ghosts_in) {
             // the neighbours' last pushes of the previous replica on this context must have landed before
@@ -1084,7 +1087,8 @@ static int run_batch(ising_ctx* ctx_a, ising_ctx* ctx_b, int nrep, const uint32_
         e = cudaMemcpyAsync(local_row(c, d, 0, 0), black_in[k], bytes, cudaMemcpyHostToDevice, d.stream);
         if (e == cudaSuccess) e = cudaMemcpyAsync(local_row(c, d, 1, 0), white_in[k], bytes, cudaMemcpyHostToDevice, d.stream);
         // compute of job k starts when compute of job k-1 (other context) is done
-        if (e == cudaSuccess && k > 0 && cs[0] != cs[1]) e = cudaStreamWaitEvent(d.stream, cs[(k - 1) & 1]->dev[0].ev_color, 0);
+        if (e == cudaSuccess && k > 0 && cs[(k - 1) % nctx] != c)
+            e = cudaStreamWaitEvent(d.stream, cs[(k - 1) % nctx]->dev[0].ev_color, 0);
         if (e != cudaSuccess) break;
         rc = ising_sweeps(c, first_it, n);
         if (rc != ISING_OK) break;
@@ -1100,7 +1104,7 @@ static int run_batch(ising_ctx* ctx_a, ising_ctx* ctx_b, int nrep, const uint32_
         if (e == cudaSuccess && black_out && black_out[k]) e = cudaMemcpyAsync(black_out[k], local_row(c, d, 0, 0), bytes, cudaMemcpyDeviceToHost, d.stream);
         if (e == cudaSuccess && white_out && white_out[k]) e = cudaMemcpyAsync(white_out[k], local_row(c, d, 1, 0), bytes, cudaMemcpyDeviceToHost, d.stream);
     }
-    for (ising_ctx* c : cs) {   // always drain both streams before the staging buffers go away
+    for (ising_ctx* c : cs) {   // always drain every stream before the staging buffers go away
         cudaError_t es = cudaStreamSynchronize(c->dev[0].stream);
         if (e == cudaSuccess) e = es;
     }
@@ -1117,7 +1121,15 @@ int ising_run_batch_from_host(ising_ctx* ctx_a, ising_ctx* ctx_b, int nrep, cons
                               const uint32_t* const* white_in, int first_it, int n, uint32_t* const* black_out,
                               uint32_t* const* white_out, uint64_t* up, uint64_t* down)
 {
-    return run_batch(ctx_a, ctx_b, nrep, black_in, white_in, nullptr, first_it, n, black_out, white_out, up, down);
+    ising_ctx* cs[2] = {ctx_a, ctx_b ? ctx_b : ctx_a};
+    return run_batch(cs, 2, nrep, black_in, white_in, nullptr, first_it, n, black_out, white_out, up, down);
+}
+
+int ising_run_batch_from_host_n(ising_ctx* const* ctxs, int nctx, int nrep, const uint32_t* const* black_in,
+                                const uint32_t* const* white_in, const uint32_t* const* ghosts_in, int first_it, int n,
+                                uint32_t* const* black_out, uint32_t* const* white_out, uint64_t* up, uint64_t* down)
+{
+    return run_batch(ctxs, nctx, nrep, black_in, white_in, ghosts_in, first_it, n, black_out, white_out, up, down);
 }
 
 int ising_run_slab_batch_from_host(ising_ctx* ctx_a, ising_ctx* ctx_b, int nrep, const uint32_t* const* black_in,
@@ -1125,7 +1137,8 @@ int ising_run_slab_batch_from_host(ising_ctx* ctx_a, ising_ctx* ctx_b, int nrep,
                                    uint32_t* const* black_out, uint32_t* const* white_out, uint64_t* up, uint64_t* down)
 {
     if (!ghosts_in) return fail(ISING_EINVAL, "ghosts_in is required");
-    return run_batch(ctx_a, ctx_b, nrep, black_in, white_in, ghosts_in, first_it, n, black_out, white_out, up, down);
+    ising_ctx* cs[2] = {ctx_a, ctx_b ? ctx_b : ctx_a};
+    return run_batch(cs, 2, nrep, black_in, white_in, ghosts_in, first_it, n, black_out, white_out, up, down);
 }
 
 int ising_host_alloc(size_t bytes, int write_combined, void** ptr)

@@ -82,6 +82,8 @@ def load_library():
         "ising_row_ptr": ([vp, C.c_int, C.c_int, C.c_int, C.POINTER(vp), C.POINTER(C.c_size_t)], C.c_int),
         "ising_update_color_part": ([vp, C.c_int, C.c_int, C.c_int, C.c_int, vp], C.c_int),
         "ising_host_alloc": ([C.c_size_t, C.c_int, C.POINTER(vp)], C.c_int),
+        "ising_run_batch_from_host_n": ([C.POINTER(vp), C.c_int, C.c_int, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp),
+                                         C.c_int, C.c_int, C.POINTER(vp), C.POINTER(vp), u64p, u64p], C.c_int),
         "ising_host_free": ([vp], C.c_int),
         "ising_device_count": ([C.POINTER(C.c_int)], C.c_int),
         "ising_device_info": ([C.c_int, C.c_char_p, C.c_size_t] + [C.POINTER(C.c_int)] * 5, C.c_int),
@@ -124,7 +126,7 @@ EXPORTED_SYMBOLS = ("ising_create ising_destroy ising_last_error ising_abi_versi
                     "ising_export_bonds_ref_layout ising_export_ref_layout "
                     "ising_import_ref_layout ising_export_bits ising_import_bits ising_dump_lattice "
                     "ising_save_checkpoint ising_load_checkpoint "
-                    "ising_run_from_host ising_run_batch_from_host ising_run_slab_batch_from_host ising_row_ptr ising_update_color_part ising_host_alloc ising_host_free ising_accept_count "
+                    "ising_run_from_host ising_run_batch_from_host ising_run_slab_batch_from_host ising_row_ptr ising_update_color_part ising_host_alloc ising_host_free ising_run_batch_from_host_n ising_accept_count "
                     "ising_device_count ising_device_info ising_can_access_peer "
                     "ising_ipc_export ising_ipc_attach ising_push_edges "
                     "ising_accept_table ising_site_random ising_launch_count ising_kernel_name "
@@ -356,6 +358,14 @@ class IsingEngine:
                 return None
             return (C.c_void_p * k)(*[(a.ctypes.data if a is not None else None) for a in arrs])
         up, dn = (C.c_uint64 * k)(), (C.c_uint64 * k)()
+        if isinstance(other, (list, tuple)):      # more than two contexts: job j runs on [self] + other, round robin
+            hs = [self._h] + [o._h for o in other]
+            arr = (C.c_void_p * len(hs))(*[h.value if hasattr(h, "value") else h for h in hs])
+            if ghosts_in is not None:
+                assert len(ghosts_in) == k and all(g.shape == (2, self.pitch) and g.dtype == np.uint32 for g in ghosts_in)
+            self._ck(self._L.ising_run_batch_from_host_n(arr, len(hs), k, ptrs(black_in), ptrs(white_in), ptrs(ghosts_in),
+                                                         int(first_it), int(n), ptrs(black_out), ptrs(white_out), up, dn))
+            return [(int(up[i]), int(dn[i])) for i in range(k)]
         oh = other._h if other is not None else None
         if ghosts_in is None:
             self._ck(self._L.ising_run_batch_from_host(self._h, oh, k, ptrs(black_in), ptrs(white_in), int(first_it),

@@ -256,13 +256,14 @@ class SlabEngine:
 
     def run_batch_from_host(self, other, black_in, white_in, ghosts_in, n, black_out=None, white_out=None):
         """Replica batch on this rank's slab (see IsingEngine.run_batch_from_host); `other` is a second
-        SlabEngine of the same shape on the same GPU.  Every rank of the group must make the same call."""
+        SlabEngine of the same shape on the same GPU, or a list of them (jobs round-robin over [self] + other).
+        Every rank of the group must make the same call."""
+        oe = [o.eng for o in other] if isinstance(other, (list, tuple)) else (other.eng if other else None)
         if self.world == 1:
-            return self.eng.run_batch_from_host(other.eng if other else None, black_in, white_in, n, black_out, white_out,
-                                                first_it=self.it + 1)
+            return self.eng.run_batch_from_host(oe, black_in, white_in, n, black_out, white_out, first_it=self.it + 1)
         if not self.fused:
             raise ValueError("replica batches over several slabs need halo='fused'")
-        return self.eng.run_batch_from_host(other.eng if other else None, black_in, white_in, n, black_out, white_out,
+        return self.eng.run_batch_from_host(oe, black_in, white_in, n, black_out, white_out,
                                             first_it=self.it + 1, ghosts_in=ghosts_in)
 
     def count_spins(self):

@@ -19,8 +19,11 @@ temp, seed = 2.269185, 463463564571
 eng = SlabEngine(X, Y, temp, seed, rank=rank, world=world, device=local, halo="fused")
 with torch.cuda.stream(torch.cuda.Stream()):
     eng2 = SlabEngine(X, Y, temp, seed, rank=rank, world=world, device=local, halo="fused")
+with torch.cuda.stream(torch.cuda.Stream()):
+    eng3 = SlabEngine(X, Y, temp, seed, rank=rank, world=world, device=local, halo="fused")
 eng.init_lattice()
 eng2.init_lattice()
+eng3.init_lattice()
 rng = np.random.default_rng(100 + rank)
 reps, want = [], []
 for k in range(nrep):       # different lattices per replica: the plain path gives ghosts and expected results
@@ -34,14 +37,16 @@ for k in range(nrep):       # different lattices per replica: the plain path giv
     torch.cuda.synchronize()
     want.append(eng.eng.export_bits() + (eng.count_spins(),))
     reps.append((b, w, g))
-eng.it = eng2.it = 0
-torch.cuda.synchronize()
-dist.barrier()
-ob = [np.zeros((Y, X // 64), np.uint32) for _ in reps]
-ow = [np.zeros((Y, X // 64), np.uint32) for _ in reps]
-counts = eng.run_batch_from_host(eng2, [r[0] for r in reps], [r[1] for r in reps], [r[2] for r in reps], sweeps, ob, ow)
-ok = all(np.array_equal(ob[k], want[k][0]) and np.array_equal(ow[k], want[k][1]) and counts[k] == want[k][2]
-         for k in range(nrep))
+ok = True
+for other in (eng2, [eng2, eng3]):          # two contexts per rank, then three (ising_run_batch_from_host_n)
+    eng.it = eng2.it = eng3.it = 0
+    torch.cuda.synchronize()
+    dist.barrier()
+    ob = [np.zeros((Y, X // 64), np.uint32) for _ in reps]
+    ow = [np.zeros((Y, X // 64), np.uint32) for _ in reps]
+    counts = eng.run_batch_from_host(other, [r[0] for r in reps], [r[1] for r in reps], [r[2] for r in reps], sweeps, ob, ow)
+    ok = ok and all(np.array_equal(ob[k], want[k][0]) and np.array_equal(ow[k], want[k][1]) and counts[k] == want[k][2]
+                    for k in range(nrep))
 open(os.path.join(out, "ok%d" % rank), "w").write("1" if ok else "0")
 dist.barrier()
 dist.destroy_process_group()

@@ -142,8 +142,8 @@ def test_replica_batch_from_host_matches_oracle(ig, oracle):
         ora.sweeps(n, TC)
         want.append((ora.export_bits(0), ora.export_bits(1), ora.count()))
         ora.close()
-    with ig.IsingEngine(X, Y, temp=TC) as ea, ig.IsingEngine(X, Y, temp=TC) as eb:
-        for other in (eb, None):
+    with ig.IsingEngine(X, Y, temp=TC) as ea, ig.IsingEngine(X, Y, temp=TC) as eb, ig.IsingEngine(X, Y, temp=TC) as ec:
+        for other in (eb, None, [eb, ec], []):      # 2 contexts, 1, 3 (ising_run_batch_from_host_n), 1 through _n
             ob = [np.zeros((Y, X // 64), np.uint32) for _ in starts]
             ow = [np.zeros((Y, X // 64), np.uint32) for _ in starts]
             counts = ea.run_batch_from_host(other, [s[0] for s in starts], [s[1] for s in starts], n, ob, ow)
