@@ -627,20 +627,33 @@ tc_update_pipe_kernel(const __grid_constant__ CUtensorMap lat_map, const __grid_
         // ---------------- MMA issuer: one thread drives the tensor core ------------------------
         if (lane == 0) {
             const uint32_t aK = smem_addr(sK), aE = smem_addr(sE);
+            const int a = first & 1, b = p.is_black ? a : 1 - a;   // parities of every sub-block of this CTA (stride, 2nbx
+                                                                   // and ntiles are even, so tile & 1 == first & 1)
+            // k-step of a K-major operand = 32 bytes inside the 128-byte rows, of an MN-major one = 32 rows
+            const uint32_t kh_step = (a == 0) ? 4096u : 32u, kv_step = (b == 0) ? 4096u : 32u;
+            const uint32_t idesc_h = IDESC_I8(0, a == 0, PIPE_HALF_COLS), idesc_v = IDESC_I8(b == 0, 1, PIPE_HALF_COLS);
+            const uint32_t idesc_e = IDESC_I8(0, 1, PIPE_HALF_COLS);
+            // columns 64*hf .. of the B operands: 64 rows on in a K-major tile, 64 bytes on in an MN-major one
+            const uint32_t nh_step = (a == 0) ? (uint32_t)PIPE_HALF_COLS : (uint32_t)PIPE_HALF_COLS * 128u;
+            // descriptors: everything that does not depend on the stage is built once; a byte offset inside the
+            // 256 KiB window is an add of offset / 16 to the low word of a descriptor
+            uint64_t dKh[PIPE_HALVES][4], dKv[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                dKv[k] = umma_desc_sw128(aK + kv_step * k);
+#pragma unroll
+                for (int hf = 0; hf < PIPE_HALVES; hf++) dKh[hf][k] = umma_desc_sw128(aK + kh_step * k + nh_step * hf);
+            }
+            const uint64_t dE = umma_desc_sw128(aE + (b == 0 ? 0u : 32u));
+            const uint64_t dH0 = umma_desc_sw128(smem_addr(sHV));      // stage 0; stage s: + s * PIPE_STAGE_BYTES / 16
             mbar_wait_parity(&k_bar, 0);
             int it = 0;
+#pragma unroll 1
             for (int tile = first; tile < ntiles; tile += stride, ++it) {
                 const int s = it & (PIPE_STAGES - 1);
                 const uint32_t ph = (uint32_t)(it / PIPE_STAGES) & 1u;
-                const int a = tile & 1, b = p.is_black ? a : 1 - a;   // parities of the sub-block (2nbx and ntiles are even)
                 mbar_wait_parity(&full_bar[s], ph);                               // operands landed
-                const uint32_t aH = smem_addr(sHV + s * PIPE_STAGE_BYTES), aV = aH + TILE_BYTES;
-                // k-step of a K-major operand = 32 bytes inside the 128-byte rows, of an MN-major one = 32 rows
-                const uint32_t kh_step = (a == 0) ? 4096u : 32u, kv_step = (b == 0) ? 4096u : 32u;
-                const uint32_t idesc_h = IDESC_I8(0, a == 0, PIPE_HALF_COLS), idesc_v = IDESC_I8(b == 0, 1, PIPE_HALF_COLS);
-                const uint32_t idesc_e = IDESC_I8(0, 1, PIPE_HALF_COLS);
-                // columns 64*hf .. of the B operands: 64 rows on in a K-major tile, 64 bytes on in an MN-major one
-                const uint32_t nh_step = (a == 0) ? (uint32_t)PIPE_HALF_COLS : (uint32_t)PIPE_HALF_COLS * 128u;
+                const uint64_t dH = dH0 + (uint64_t)(s * (PIPE_STAGE_BYTES >> 4)), dV = dH + (TILE_BYTES >> 4);
 #pragma unroll
                 for (int hf = 0; hf < PIPE_HALVES; hf++) {
                     if (it >= PIPE_STAGES) mbar_wait_parity(&free_bar[s][hf], ph ^ 1u);   // accumulator (half) drained
@@ -649,13 +662,13 @@ tc_update_pipe_kernel(const __grid_constant__ CUtensorMap lat_map, const __grid_
                     const uint32_t acc = tmem_d + (uint32_t)(s * SUBN + hf * PIPE_HALF_COLS);
 #pragma unroll
                     for (int k = 0; k < 4; k++)      // H (K-major A) x Kh (B): nn[j][i] = H[j][i] + H[j][i+di]
-                        umma_i8(acc, umma_desc_sw128(aH + 32 * k), umma_desc_sw128(aK + kh_step * k + nh_step * hf), idesc_h, k > 0);
+                        umma_i8(acc, dH + 2 * k, dKh[hf][k], idesc_h, k > 0);
 #pragma unroll
                     for (int k = 0; k < 4; k++)      // Kv (A) x V (MN-major B, in place): += V[j][i] + V[j+dj][i]
-                        umma_i8(acc, umma_desc_sw128(aK + kv_step * k), umma_desc_sw128(aV + 4096 * k + PIPE_HALF_COLS * hf), idesc_v, 1u);
+                        umma_i8(acc, dKv[k], dV + (4096 >> 4) * k + ((PIPE_HALF_COLS * hf) >> 4), idesc_v, 1u);
                     // fifth k-step: rows 128.. of V = the edge row (the other 31 rows meet zero columns of E):
                     // E (K-major, slice b) x V''  adds the row above to row 0 (b == 0) or the row below to row 127
-                    umma_i8(acc, umma_desc_sw128(aE + (b == 0 ? 0u : 32u)), umma_desc_sw128(aV + 4096 * 4 + PIPE_HALF_COLS * hf), idesc_e, 1u);
+                    umma_i8(acc, dE, dV + (4096 >> 4) * 4 + ((PIPE_HALF_COLS * hf) >> 4), idesc_e, 1u);
                     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
                                      smem_addr(&mma_bar[s][hf]))
                                  : "memory");
