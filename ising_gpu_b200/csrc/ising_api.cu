@@ -261,7 +261,16 @@ int ising_abi_version(void) { return ISING_B200_ABI_VERSION; }
 uint64_t ising_accept_count(float p, int strict) { return accept_count(p, strict != 0); }
 void ising_accept_table(float temp, float out[5]) { accept_table(temp, out); }
 uint64_t ising_launch_count(const ising_ctx* ctx) { return ctx ? ctx->launches : 0; }
-const char* ising_kernel_name(const ising_ctx* ctx) { return update_kernel_name(ctx ? ctx->rule.fast : 1); }
+// name of the kernel that updates the bulk of this context's lattice (launch_part picks per launch)
+const char* ising_kernel_name(const ising_ctx* ctx)
+{
+    if (!ctx) return update_kernel_name(1, 0);
+    const int tiles_y = ctx->cfg.Y / TH;
+    const int bulk_rows = ctx->fused ? tiles_y - 2 : tiles_y;     // fused: the interior launch
+    const bool two = ctx->two_tiles && !ctx->persistent && !ctx->bonds && bulk_rows > 0 && (bulk_rows % 2) == 0 &&
+                     (ctx->yperiod == 0 || ctx->yperiod % (2 * TH) == 0);
+    return update_kernel_name(ctx->rule.fast, two ? 0 : (ctx->persistent ? 2 : 1));
+}
 
 int ising_device_count(int* count)
 {

@@ -770,10 +770,19 @@ void launch_update2(const CUtensorMap& src_tile2, const CUtensorMap& src_row, co
     else             update_color_kernel2<false><<<grid, UPDATE_THREADS, 0, stream>>>(src_tile2, src_row, src_side2, dst, p);
 }
 
-const char* update_kernel_name(int fast)
+const char* update_kernel_name(int fast, int variant)
 {
-    return fast ? "update_color_kernel2<fast: 2 integer thresholds, TMA 32x32-word tiles, 2 Philox streams per thread, 1 bit/spin>"
-                : "update_color_kernel2<generic acceptance rule, TMA 32x32-word tiles, 2 Philox streams per thread, 1 bit/spin>";
+    switch (variant) {
+        case 1:
+            return fast ? "update_color_kernel<fast: 2 integer thresholds, TMA 16x32-word tiles, 1 bit/spin>"
+                        : "update_color_kernel<generic acceptance rule, TMA 16x32-word tiles, 1 bit/spin>";
+        case 2:
+            return fast ? "update_color_persistent<fast: 2 integer thresholds, 8-stage TMA ring of 16x32-word tiles, 1 bit/spin>"
+                        : "update_color_persistent<generic acceptance rule, 8-stage TMA ring of 16x32-word tiles, 1 bit/spin>";
+        default:
+            return fast ? "update_color_kernel2<fast: 2 integer thresholds, TMA 32x32-word tiles, 2 Philox streams per thread, 1 bit/spin>"
+                        : "update_color_kernel2<generic acceptance rule, TMA 32x32-word tiles, 2 Philox streams per thread, 1 bit/spin>";
+    }
 }
 
 // ------------------------------------------------------------------------------------------

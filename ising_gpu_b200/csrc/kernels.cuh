@@ -120,6 +120,7 @@ void launch_halo_wait(const unsigned int* flags, unsigned int want0, unsigned in
 void launch_update_persistent(const CUtensorMap& src_tile, const CUtensorMap& src_row, const CUtensorMap& src_side,
                               const CUtensorMap& dst_tile, uint32_t* dst_local_row0, const uint32_t* bond_planes,
                               UpdateParams p, int tiles_x, int tile_rows, int sms, cudaStream_t stream);
-const char* update_kernel_name(int fast);
+// variant: 0 = two tiles per CTA (kernel2), 1 = one tile per CTA, 2 = persistent
+const char* update_kernel_name(int fast, int variant);
 
 }  // namespace ising
