@@ -460,7 +460,15 @@ static_assert(PIPE_STAGES * SUBN <= 512, "TMEM has 512 columns");
 constexpr int PIPE_MAXREG = (PIPE_CONSUMER_WARPS <= 16) ? 96 : 72;
 // with 96 registers and 64 columns per thread the tile's own spins are prefetched into registers one tile
 // ahead; otherwise they are prefetched into L2 and loaded at the start of the tile
-constexpr bool PIPE_REG_PREFETCH = (PIPE_MAXREG == 96 && PIPE_COLS == 64);
+// ISING_TC_EARLY_FREE: the sums of the second half of a thread's columns are fetched from TMEM together, at the
+// half-way point of the tile, so that the accumulator is handed back after 50 % instead of 75 % of the tile's work
+// (more room for the warps of a group to drift).  Needs 16 more registers for the sums; they are taken from the
+// register prefetch of the next tile's own spins (L2 prefetch + loads at the start of the tile instead).
+#ifndef ISING_TC_EARLY_FREE
+#define ISING_TC_EARLY_FREE 0
+#endif
+constexpr bool PIPE_EARLY_FREE = ISING_TC_EARLY_FREE && (PIPE_COLS == 64);
+constexpr bool PIPE_REG_PREFETCH = (PIPE_MAXREG == 96 && PIPE_COLS == 64) && !(PIPE_EARLY_FREE && ISING_TC_EARLY_FREE == 1);
 constexpr int PIPE_CHUNKS = PIPE_COLS / 16;             // 16-byte chunks = TMEM column groups per thread
 // Build option (off): hand the accumulators over per COLUMN HALF -- every tile multiplied as two M=128, N=64
 // products with their own mma[] / free[] barriers, so that a warp only waits for the three other warps that share
@@ -756,24 +764,47 @@ tc_update_pipe_kernel(const __grid_constant__ CUtensorMap lat_map, const __grid_
             mbar_wait_parity(&mma_bar[s][hf], ph);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 
-#pragma unroll
-            for (int gq = 0; gq < PIPE_CHUNKS; gq++) {  // groups of 16 columns
-                uint32_t r[16];
-                const int col0 = colbase + 16 * gq;
-                const uint32_t taddr = tmem_d + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(s * SUBN + col0);
+            uint32_t rr[2][16];
+            auto tmem_ld = [&](int gq, uint32_t (&r)[16]) {    // asynchronous: tmem_wait() before the values are used
+                const uint32_t taddr = tmem_d + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(s * SUBN + colbase + 16 * gq);
                 asm volatile(
                     "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-                    "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
-                    "tcgen05.wait::ld.sync.aligned;"
+                    "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
                     : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
                       "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
                     : "r"(taddr)
                     : "memory");
+            };
+            auto tmem_wait = [&](uint32_t (&r)[16]) {          // the registers are operands so that no use can move above
+                asm volatile("tcgen05.wait::ld.sync.aligned;"
+                             : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                               "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+                             :
+                             : "memory");
+            };
+#pragma unroll
+            for (int gq = 0; gq < PIPE_CHUNKS; gq++) {  // groups of 16 columns
+                uint32_t (&r)[16] = rr[gq & 1];
+                const int col0 = colbase + 16 * gq;
+                bool last_ld;                           // the accumulator has been read completely
+                if (PIPE_EARLY_FREE && gq >= PIPE_CHUNKS - 2) {
+                    if (gq == PIPE_CHUNKS - 2) {        // both remaining groups at once
+                        tmem_ld(gq, rr[gq & 1]);
+                        tmem_ld(gq + 1, rr[(gq + 1) & 1]);
+                        tmem_wait(rr[0]);
+                        tmem_wait(rr[1]);
+                    }
+                    last_ld = (gq == PIPE_CHUNKS - 2);
+                } else {
+                    tmem_ld(gq, r);
+                    tmem_wait(r);
+                    last_ld = (gq == PIPE_CHUNKS - 1);
+                }
                 // terms from across the sub-block edge (add_boundaries)
                 if (col0 == 0 && edge_col == 0) r[0] += (uint32_t)edge_h;
                 if (col0 == SUBN - 16 && edge_col == SUBN - 1) r[15] += (uint32_t)edge_h;
-                if (gq == PIPE_CHUNKS - 1) {
-                    // this warp is done with accumulator s and with its edge row: hand the accumulator back
+                if (last_ld) {
+                    // this warp is done with accumulator s: hand it back
                     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                     __syncwarp();
                     if (lane == 0)
