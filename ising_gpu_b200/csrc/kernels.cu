@@ -176,19 +176,37 @@ __device__ __forceinline__ void word_reject_masks(const ThreadConsts& tc, const 
     rejB = b;
 }
 
-// Flip mask of one word from its own spins, the four neighbour words and the reject masks.
-template <bool FAST>
-__device__ __forceinline__ uint32_t flip_mask(uint32_t me, uint32_t up, uint32_t dn, uint32_t ct, uint32_t sd,
-                                              uint32_t rejA, uint32_t rejB, const AcceptRule& r)
+template <int LUT>
+__device__ __forceinline__ uint32_t lop3(uint32_t a, uint32_t b, uint32_t c)
 {
-    // d_k = neighbour_k ^ me = 1 where anti-aligned; (g,p) and (g2,p2) are the 2-bit sums of pairs
-    const uint32_t p = up ^ dn, g = (up ^ me) & (dn ^ me);
-    const uint32_t p2 = ct ^ sd, g2 = (ct ^ me) & (sd ^ me);
+    uint32_t d;
+    asm("lop3.b32 %0, %1, %2, %3, %4;" : "=r"(d) : "r"(a), "r"(b), "r"(c), "n"(LUT));
+    return d;
+}
+
+// New value of one word from its own spins, the four neighbour words and the reject masks.
+template <bool FAST>
+__device__ __forceinline__ uint32_t updated_word(uint32_t me, uint32_t up, uint32_t dn, uint32_t ct, uint32_t sd,
+                                                 uint32_t rejA, uint32_t rejB, const AcceptRule& r)
+{
     if (FAST) {
-        const uint32_t none = ~(p | g | p2 | g2);       // 4 aligned: dE = +8 -> slot B
-        const uint32_t one = (p ^ p2) & ~(g | g2);      // 3 aligned: dE = +4 -> slot A
-        return ~((one & rejA) | (none & rejB));          // everything else always flips
+        // Eight hand-picked LOP3 (the compiler needs 11-12 for the pair-sum formulation below, and every ALU
+        // instruction is 2 cycles of the binding resource).  With z1 / z2 = both vertical / both
+        // horizontal neighbours aligned with the site, and up ^ dn / ct ^ sd = exactly one of a pair anti-aligned:
+        //   keep = z2 & ((z1 & rejB) | ((up ^ dn) & rejA))  |  z1 & (ct ^ sd) & rejA      (dE = +8: slot B, +4: slot A)
+        // everything else flips: new = me ^ ~keep, straight out of the last LOP3.
+        const uint32_t z1 = lop3<0x81>(up, dn, me);            // ~(up ^ me) & ~(dn ^ me)
+        const uint32_t z2 = lop3<0x81>(ct, sd, me);
+        const uint32_t a1 = lop3<0x28>(up, dn, rejA);          // (up ^ dn) & rejA
+        const uint32_t a2 = lop3<0x28>(ct, sd, rejA);
+        const uint32_t u = lop3<0xEA>(z1, rejB, a1);           // (z1 & rejB) | a1
+        const uint32_t v = z2 & u;
+        const uint32_t x = z1 & a2;
+        return lop3<0xE1>(me, v, x);                           // ~(me ^ (v | x))
     } else {
+        // d_k = neighbour_k ^ me = 1 where anti-aligned; (g,p) and (g2,p2) are the 2-bit sums of pairs
+        const uint32_t p = up ^ dn, g = (up ^ me) & (dn ^ me);
+        const uint32_t p2 = ct ^ sd, g2 = (ct ^ me) & (sd ^ me);
         const uint32_t c = p & p2;
         const uint32_t b0 = p ^ p2, b1 = g ^ g2 ^ c, b2 = g & g2;   // b = number anti-aligned
         const uint32_t accA = ~rejA, accB = ~rejB;
@@ -197,7 +215,7 @@ __device__ __forceinline__ uint32_t flip_mask(uint32_t me, uint32_t up, uint32_t
         uint32_t f = 0;
 #pragma unroll
         for (int b = 0; b < 5; b++) f |= cls[b] & (r.always[b] | (r.selA[b] & accA) | (r.selB[b] & accB));
-        return f;
+        return me ^ f;
     }
 }
 
@@ -330,7 +348,7 @@ update_color_kernel(const __grid_constant__ CUtensorMap src_tile, const __grid_c
             if (read_back) { sd ^= jb[j][2]; ct ^= jb[j][3]; }   // sd = left neighbour, ct = right
             else           { ct ^= jb[j][2]; sd ^= jb[j][3]; }   // ct = left neighbour, sd = right
         }
-        me[j] ^= flip_mask<FAST>(me[j], up, dn, ct, sd, rejA[j], rejB[j], p.rule);
+        me[j] = updated_word<FAST>(me[j], up, dn, ct, sd, rejA[j], rejB[j], p.rule);
         my[16 * j] = me[j];
     }
     if (PUSH && (y0 == 0 || y0 + TH == p.rows)) {   // CTA-uniform: only the two edge tile rows push
@@ -488,7 +506,7 @@ update_color_kernel2(const __grid_constant__ CUtensorMap src_tile2 /* box 32 x 3
                 const uint32_t next = (w == TW - 1) ? sR[r * SIDE_W] : sV[(r + 1) * TW + w + 1];
                 sd = __funnelshift_r(ct, next, 1);    // (ct >> 1) | (next << 31)
             }
-            me[t][j] ^= flip_mask<FAST>(me[t][j], up, dn, ct, sd, rejA[j][t], rejB[j][t], p.rule);
+            me[t][j] = updated_word<FAST>(me[t][j], up, dn, ct, sd, rejA[j][t], rejB[j][t], p.rule);
             my[t * lower + 16 * j] = me[t][j];
         }
     }
@@ -694,7 +712,7 @@ update_color_persistent(const __grid_constant__ CUtensorMap src_tile, const __gr
                 if (read_back) { sd[j] ^= jb[j][2]; ct[j] ^= jb[j][3]; }   // sd = left neighbour, ct = right
                 else           { ct[j] ^= jb[j][2]; sd[j] ^= jb[j][3]; }   // ct = left neighbour, sd = right
             }
-            me[j] ^= flip_mask<FAST>(me[j], up[j], dn[j], ct[j], sd[j], rejA[j], rejB[j], p.rule);
+            me[j] = updated_word<FAST>(me[j], up[j], dn[j], ct[j], sd[j], rejA[j], rejB[j], p.rule);
             my[16 * j] = me[j];
         }
         if (PUSH && (y0 == 0 || y0 + TH == p.rows)) {   // CTA-uniform: only the two edge tile rows push
