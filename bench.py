@@ -400,6 +400,7 @@ def run_b200(a):
             ready = False
         ready = bool(-allmax(-float(ready))[0])           # every rank enters the batch, or none does
         runs_dl, runs = [], []
+        e2e_clocks = {}
         ok = False
         api = None
         if ready and world == 1:
@@ -458,12 +459,15 @@ def run_b200(a):
             def timed(download):
                 batch(max(NCTX, 8), download)        # untimed: every context touched, clocks back up after host-side checks
                 out = []
+                smp = ClockSampler(local) if rank == 0 else None
                 for _ in range(3):                   # three runs of K steps, all reported; the best one is the value
                     barrier()                        # (the reference arm does the same)
                     t0 = time.perf_counter()
                     counts = batch(ksteps, download)
                     barrier()
                     out.append(time.perf_counter() - t0)
+                if smp:
+                    e2e_clocks["with_lattice_download" if download else "counts_only"] = smp.stop()
                 return out, counts
             runs_dl, counts = timed(True)            # D2H of the final planes as well (a checkpoint per step)
             if world == 1:
@@ -501,6 +505,7 @@ def run_b200(a):
                    "timer": "host monotonic clock around the synchronised region, max over ranks; three runs of %d steps, "
                             "the best one is `value`" % ksteps,
                    "runs": [round(flips_e2e / (x * 1e9), 2) for x in runs], "api": api, "numa_of_rank0": numa, "input_staging": a.staging, "contexts_per_gpu": NCTX,
+                   "clocks": e2e_clocks,
                    "with_lattice_download": {"value": round(flips_e2e / (min(runs_dl) * 1e9), 2), "unit": "flips/ns",
                                              "runs": [round(flips_e2e / (x * 1e9), 2) for x in runs_dl],
                                              "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": (2 * plane_bytes + 8) * world},
