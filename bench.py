@@ -289,8 +289,10 @@ def run_b200(a):
     if selfcheck is not None and not selfcheck["ok"]:
         raise SystemExit("selfcheck failed: the slab decomposition does not reproduce the 1-GPU lattice: %r" % (selfcheck,))
 
-    eng = SlabEngine(X_COLS, rows, TEMP, a.seed, rank=rank, world=world, device=local, overlap=not a.no_overlap,
-                     halo=a.halo)
+    work = torch.cuda.Stream() if a.own_stream else torch.cuda.current_stream()
+    with torch.cuda.stream(work):
+        eng = SlabEngine(X_COLS, rows, TEMP, a.seed, rank=rank, world=world, device=local, overlap=not a.no_overlap,
+                         halo=a.halo)
 
     def total_counts():
         up, dn = eng.count_spins()
@@ -326,10 +328,10 @@ def run_b200(a):
     launches0 = eng.eng.launches
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
-    e0.record()
+    e0.record(work)                     # events on the stream the kernels are launched on
     for _ in range(a.steps):
         eng.sweeps(S)
-    e1.record()
+    e1.record(work)
     barrier()
     ms = e0.elapsed_time(e1)
     launches = eng.eng.launches - launches0
@@ -690,6 +692,9 @@ def main():
     ap.add_argument("--e2e-contexts", type=int, default=3,
                     help="contexts per GPU the e2e replica batch rotates over (2: a download and the next upload share "
                          "one job's compute time; 3: they have two)")
+    ap.add_argument("--own-stream", type=int, default=0, help="1: the lattice works on its own non-blocking stream; "
+                                                              "0: on torch's current (default) stream.  No measurable "
+                                                              "difference, e2e hiccups included (profiles/r02_e2e_noise.txt)")
     ap.add_argument("--staging", default="pinned", choices=["pinned", "wc"],
                     help="e2e input buffers: plain page-locked memory, or write-combined (ising_host_alloc)")
     ap.add_argument("--no-tc", action="store_true", help="skip the tensor-core variant leg (variants.tensorcore)")
