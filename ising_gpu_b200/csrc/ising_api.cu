@@ -101,6 +101,11 @@ struct ising_ctx {
     AcceptRule rule;
     uint32_t thr_half = 0;
     uint64_t launches = 0;
+    // replica batches: per-job up-counts on the device and their pinned landing zone, kept between calls (allocating
+    // and freeing page-locked memory inside every batch call is a device-wide synchronisation in the timed path)
+    unsigned long long* batch_h_counts = nullptr;
+    unsigned long long* batch_d_counts = nullptr;
+    int batch_counts_cap = 0;
     std::vector<DevState> dev;
 };
 
@@ -430,6 +435,11 @@ int ising_create(const ising_cfg* cfg, ising_ctx** out)
 int ising_destroy(ising_ctx* c)
 {
     if (!c) return ISING_OK;
+    if (!c->dev.empty() && (c->batch_h_counts || c->batch_d_counts)) {
+        cudaSetDevice(c->dev[0].device);
+        if (c->batch_h_counts) cudaFreeHost(c->batch_h_counts);
+        if (c->batch_d_counts) cudaFree(c->batch_d_counts);
+    }
     for (DevState& d : c->dev) {
         cudaSetDevice(d.device);
         if (d.stream) cudaStreamSynchronize(d.stream);
@@ -1063,11 +1073,19 @@ static int run_batch(ising_ctx* const* ctxs, int nctx, int nrep, const uint32_t*
     unsigned long long* h_counts = nullptr;      // pinned landing zone of the per-job up-counts
     unsigned long long* d_counts = nullptr;
     if (up && down && nrep > 0) {
-        CU_TRY(cudaHostAlloc((void**)&h_counts, sizeof(unsigned long long) * nrep, cudaHostAllocDefault));
-        cudaError_t e = cudaMalloc((void**)&d_counts, sizeof(unsigned long long) * nrep);
-        if (e == cudaSuccess) e = cudaMemsetAsync(d_counts, 0, sizeof(unsigned long long) * nrep, cs[0]->dev[0].stream);
-        if (e == cudaSuccess) e = cudaStreamSynchronize(cs[0]->dev[0].stream);
-        if (e != cudaSuccess) { cudaFreeHost(h_counts); cudaFree(d_counts); return fail(ISING_ECUDA, "batch counters: %s", cudaGetErrorString(e)); }
+        if (ctx_a->batch_counts_cap < nrep) {        // (re)allocate the counters owned by the first context
+            if (ctx_a->batch_h_counts) cudaFreeHost(ctx_a->batch_h_counts);
+            if (ctx_a->batch_d_counts) cudaFree(ctx_a->batch_d_counts);
+            ctx_a->batch_h_counts = nullptr; ctx_a->batch_d_counts = nullptr; ctx_a->batch_counts_cap = 0;
+            const int cap = nrep < 64 ? 64 : nrep;
+            CU_TRY(cudaHostAlloc((void**)&ctx_a->batch_h_counts, sizeof(unsigned long long) * cap, cudaHostAllocDefault));
+            CU_TRY(cudaMalloc((void**)&ctx_a->batch_d_counts, sizeof(unsigned long long) * cap));
+            ctx_a->batch_counts_cap = cap;
+        }
+        h_counts = ctx_a->batch_h_counts;
+        d_counts = ctx_a->batch_d_counts;
+        // zeroed on the stream of the first job; the count kernels of later jobs follow it through the event chain
+        CU_TRY(cudaMemsetAsync(d_counts, 0, sizeof(unsigned long long) * nrep, cs[0]->dev[0].stream));
     }
     int rc = ISING_OK;
     cudaError_t e = cudaSuccess;
@@ -1119,8 +1137,6 @@ static int run_batch(ising_ctx* const* ctxs, int nctx, int nrep, const uint32_t*
     }
     if (h_counts && rc == ISING_OK && e == cudaSuccess)
         for (int k = 0; k < nrep; k++) { up[k] = h_counts[k]; down[k] = spins - h_counts[k]; }
-    if (h_counts) cudaFreeHost(h_counts);
-    if (d_counts) cudaFree(d_counts);
     if (rc != ISING_OK) return rc;
     if (e != cudaSuccess) return fail(ISING_ECUDA, "ising_run_batch_from_host: %s", cudaGetErrorString(e));
     return ISING_OK;
