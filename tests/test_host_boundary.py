@@ -108,8 +108,14 @@ def test_shipped_kernels_are_blackwell_native():
         assert tag in hs, tag
         for op in need:
             assert any(k.startswith(op) for k in hs[tag]["ops"]), (tag, op)
-    assert hs["tc_update_pipe_kernel"]["ops"]["UTCIMMA"] >= 8
+    assert hs["tc_update_pipe_kernel"]["ops"]["UTCIMMA"] >= 9          # 4 + 4 k-steps + the edge-row k-step
     assert hs["update_color_kernel_fast"]["ops"]["UTMALDG"] == 5
+    # instruction budget of the product update kernel: per thread = 128 sites = 32 Philox calls of
+    # 16 multiplies (+ 2 x 2 for the two thread ids' constants, + addressing); a regression here is a slowdown
+    k2 = hs["update_color_kernel2_fast"]["ops"]
+    assert k2["UTMALDG"] == 5
+    assert 512 <= k2["IMAD.WIDE.U32"] <= 520
+    assert k2["LOP3"] <= 640 and k2["ISETP"] <= 290
     # no mma.sync / wgmma fallbacks anywhere in the variant kernel
     assert not any(k.startswith(("HMMA", "IMMA")) for k in hs["tc_update_pipe_kernel"]["ops"])
 
