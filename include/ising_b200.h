@@ -32,7 +32,9 @@
 extern "C" {
 #endif
 
-#define ISING_B200_ABI_VERSION 1
+/* 2: + ISING_ETIMEOUT, ising_get_temperature, ising_host_alloc/free, ising_run_batch_from_host_n; checkpoint format 2;
+ *    ising_update_color_part refused on contexts with the fused halo push */
+#define ISING_B200_ABI_VERSION 2
 
 #define ISING_MAX_DEVICES 256          /* MAX_GPU, optimized/main.cu:60 */
 #define ISING_MAX_CORR_DEVICES 16      /* ising_correlation: devices of one context                     */

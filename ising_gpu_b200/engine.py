@@ -35,6 +35,9 @@ class _Cfg(C.Structure):
                 ("j_prob", C.c_float), ("reserved", C.c_int32 * 4)]
 
 
+ABI_VERSION = 2      # ISING_B200_ABI_VERSION of include/ising_b200.h
+
+
 def lib_path():
     # ISING_B200_LIB: developer override to A/B kernel variants; the product is the in-tree build
     return os.environ.get("ISING_B200_LIB") or os.path.join(_HERE, "libising_b200.so")
@@ -116,6 +119,9 @@ def load_library():
     for name, (args, res) in sig.items():
         fn = getattr(L, name)      # AttributeError here = header and library out of sync
         fn.argtypes, fn.restype = args, res
+    if L.ising_abi_version() != ABI_VERSION:      # a stale build next to newer host code: fail loudly, never guess
+        raise IsingError(-101, "%s has ABI version %d, this host code needs %d: rebuild with `make`" %
+                         (p, L.ising_abi_version(), ABI_VERSION))
     _LIB = L
     return L
 

@@ -22,7 +22,7 @@ def test_library_exports_every_declared_symbol(ig):
         assert hasattr(lib, name), "libising_b200.so does not export " + name
     from ising_gpu_b200 import engine
     assert declared == set(engine.EXPORTED_SYMBOLS)
-    assert lib.ising_abi_version() == 1
+    assert lib.ising_abi_version() == 2
 
 
 @pytest.mark.parametrize("temp", [1.5, 2.269185, 0.5, 0.3, 0.05 * 2.26918531421, 10.0, 1e9, 0.0, -1.0])
