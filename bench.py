@@ -402,6 +402,7 @@ def run_b200(a):
             ready = False
         ready = bool(-allmax(-float(ready))[0])           # every rank enters the batch, or none does
         runs_dl, runs = [], []
+        batch_error = None
         e2e_clocks = {}
         ok = False
         api = None
@@ -411,6 +412,13 @@ def run_b200(a):
             # contexts so the copies of one step overlap the kernels of the next (ising_run_batch_from_host)
             from ising_gpu_b200.engine import IsingEngine
             others = [IsingEngine(X_COLS, rows, seed=a.seed, temp=TEMP, first_device=local) for _ in range(NCTX - 1)]
+            # one unpipelined step first: the result every job of the batch must reproduce
+            it0 = eng.it
+            eng.eng.import_bits(b0, w0)
+            eng.sweeps(S)
+            want_b, want_w = eng.eng.export_bits()
+            want_counts = eng.count_spins()
+            eng.it = it0
 
             def batch(k, download):
                 return eng.eng.run_batch_from_host(others, [ins[j & 1][0] for j in range(k)],
@@ -418,9 +426,9 @@ def run_b200(a):
                                                    [outs[j % NCTX][0] for j in range(k)] if download else None,
                                                    [outs[j % NCTX][1] for j in range(k)] if download else None,
                                                    first_it=eng.it + 1)
-            want_counts = None
             api = ("ising_run_batch_from_host_n (C ABI, pinned host buffers): per step H2D of both planes, %d sweeps, "
-                   "count kernels, D2H of the spin counts; %d contexts, copies overlap the other steps' kernels" % (S, NCTX))
+                   "count kernels, D2H of the spin counts; %d contexts, copies overlap the other steps' kernels; result "
+                   "checked against the unpipelined path" % (S, NCTX))
         elif ready and a.halo == "fused":
             # the same replica batch on every rank's slab (ising_run_slab_batch_from_host): per step H2D of the
             # slab's planes and white ghost rows, S sweeps with the fused halo push between the ranks, counts,
@@ -473,12 +481,8 @@ def run_b200(a):
                     e2e_clocks["with_lattice_download" if download else "counts_only"] = smp.stop()
                 return out, counts
             runs_dl, counts = timed(True)            # D2H of the final planes as well (a checkpoint per step)
-            if world == 1:
-                ok = (len(set(counts)) == 1 and counts[0][0] + counts[0][1] == X_COLS * rows and
-                      all(np.array_equal(outs[0][0], o[0]) and np.array_equal(outs[0][1], o[1]) for o in outs[1:min(NCTX, ksteps)]))
-            else:
-                ok = all(c == want_counts for c in counts) and all(
-                    np.array_equal(ob, want_b) and np.array_equal(ow, want_w) for ob, ow in outs[:min(NCTX, ksteps)])
+            ok = all(c == want_counts for c in counts) and all(
+                np.array_equal(ob, want_b) and np.array_equal(ow, want_w) for ob, ow in outs[:min(NCTX, ksteps)])
             runs, counts2 = timed(False)             # D2H of the step's observable only
             ok = ok and counts2 == counts
             ok = bool(-allmax(-float(ok))[0])
@@ -486,8 +490,10 @@ def run_b200(a):
             runs = [allmax(x)[0] for x in runs]
             for o in others:
                 o.close()
-            if not ok:
-                raise SystemExit("e2e: pipelined replica batch does not reproduce the unpipelined result")
+            batch_error = None
+            if not ok:   # never report a number for a wrong result: the line falls back to the dependent chain and says so
+                batch_error = "pipelined replica batch did not reproduce the unpipelined result; its timings are withheld"
+                batch = None
         # dependent chain on one of the input buffers (always measured; the only e2e number without a batch)
         if outs:     # (plain page-locked buffers: the chain downloads into what it uploads next)
             outs[0][0][:], outs[0][1][:] = b0, w0
@@ -517,8 +523,8 @@ def run_b200(a):
             e2e = dict(chain)
             e2e.update({"steps": ksteps, "timer": "host monotonic clock around the synchronised region, max over ranks",
                         "numa_of_rank0": numa, "dependent_chain": chain,
-                        "note": "no replica batch on this transport (halo=%s%s)" % (a.halo, "" if ready else
-                                                                                   ", pinned host memory exhausted")})
+                        "note": batch_error or "no replica batch on this transport (halo=%s%s)" % (
+                            a.halo, "" if ready else ", pinned host memory exhausted")})
 
     out = None
     if rank == 0:
