@@ -539,8 +539,9 @@ def run_b200(a):
                 "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
                 "reference_accounting_gbs": round(achieved * REF_BYTES_PER_FLIP / ALG_BYTES_PER_FLIP, 1),
                 "binding_resource": ncu_pipe_summary(),
-                "note": "HBM-nominal path, but the bit-exact Philox4x32-10 per site makes it bound by the "
-                        "FMA-heavy pipe (IMAD.WIDE, 4 cycles/warp-instr): see DESIGN.md and profiles/"}
+                "note": "HBM-nominal path, but the bit-exact Philox4x32-10 per site makes it bound by integer issue "
+                        "(16 IMAD.WIDE + 18 LOP3 + 8 ISETP per Philox call; FMA-heavy pipe 87 % busy, the ALU/dispatch "
+                        "side binding): DESIGN.md 4.1 and profiles/update_kernel_ncu_summary.json"}
         out = {"metric": "spin-flip attempts/ns", "value": round(value, 2), "unit": "flips/ns", "n_gpus": world,
                "steps": a.steps, "warmup": a.warmup, "ms_per_step": round(ms / a.steps, 4), "higher_is_better": True,
                "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
