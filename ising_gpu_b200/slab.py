@@ -105,6 +105,25 @@ def bind_process_near_gpu(device, report=False):
     return info["gpu_node"] if bound else None
 
 
+def gather_slabs(black, white, rank, world, group=None, root=0, device=None):
+    """Stack every rank's (Y, X/64) uint32 colour planes on rank `root`, slab r = rows [r*Y, (r+1)*Y) as in the
+    reference's -d decomposition (optimized/main.cu:1542-1545): returns the two (world*Y, X/64) arrays there and
+    (None, None) on the other ranks.  Backend-agnostic like HaloExchange: host tensors over gloo, staged through
+    `device` memory over NCCL.  Every rank of the group must call it."""
+    import numpy as np
+    if world == 1:
+        return np.ascontiguousarray(black), np.ascontiguousarray(white)
+    out = []
+    for plane in (black, white):
+        t = torch.from_numpy(np.ascontiguousarray(plane, dtype=np.uint32).view(np.int32))
+        if device is not None:
+            t = t.to(device)
+        parts = [torch.empty_like(t) for _ in range(world)] if rank == root else None
+        dist.gather(t, parts, dst=root if group is None else dist.get_global_rank(group, root), group=group)
+        out.append(torch.cat(parts).cpu().numpy().view(np.uint32) if rank == root else None)
+    return out[0], out[1]
+
+
 class HaloExchange:
     def __init__(self, rank, world, group=None):
         self.rank, self.world, self.group = rank, world, group
@@ -173,6 +192,7 @@ class SlabEngine:
         `overlap`); "fused": the update kernel stores them into the neighbours' ghost rows itself
         through CUDA-IPC-mapped peer memory (ising_ipc_attach), no per-colour communication call."""
         self.rank, self.world, self.overlap = rank, world, overlap
+        self.X, self.Y, self.temp, self.seed, self.device = X, Y, temp, seed, device
         self.fused = (halo == "fused") and world > 1
         torch.cuda.set_device(device)
         self.main = torch.cuda.current_stream()
@@ -268,6 +288,40 @@ class SlabEngine:
 
     def count_spins(self):
         return self.eng.count_spins()
+
+    # -- observables of the WHOLE lattice (every rank of the group must make the same call) -----------
+    def bond_sum(self):
+        """Sum of s_i*s_j over the nearest-neighbour bonds of all slabs (ising_bond_sum per slab -- its lower
+        bonds read the white ghost rows, current after sweeps() -- added up over the ranks)."""
+        s = self.eng.bond_sum()
+        if self.world > 1:
+            t = torch.tensor([s], dtype=torch.int64, device=torch.device("cuda", self.device))
+            dist.all_reduce(t, group=self.halo.group)
+            s = int(t.item())
+        return s
+
+    def energy_per_site(self):
+        return -self.bond_sum() / float(self.world * self.Y * self.X)
+
+    def correlation(self, ncorr=128, root=0):
+        """Two-point function of the whole lattice, the reference's -c (optimized/main.cu:1072-1138 walks the slabs
+        of all devices of its one process).  ising_correlation needs every slab in one context, so the slabs' bit
+        planes (1 bit per spin) are gathered on rank `root`, loaded into a 1-device context of world*Y rows next to
+        its slab and evaluated there; every rank gets the result.  Off the hot path: print cadence only."""
+        if self.world == 1:
+            return self.eng.correlation(ncorr)
+        import numpy as np
+        torch.cuda.synchronize()
+        b, w = self.eng.export_bits()
+        B, W = gather_slabs(b, w, self.rank, self.world, self.halo.group, root, torch.device("cuda", self.device))
+        res = [None]
+        if self.rank == root:
+            with IsingEngine(self.X, self.Y * self.world, seed=self.seed, temp=self.temp, first_device=self.device) as whole:
+                whole.import_bits(B, W)
+                res[0] = np.asarray(whole.correlation(ncorr))
+        dist.broadcast_object_list(res, src=root if self.halo.group is None else dist.get_global_rank(self.halo.group, root),
+                                   group=self.halo.group)
+        return res[0]
 
     def close(self):
         self.eng.close()

@@ -163,3 +163,48 @@ def test_slab_replica_batch(tmp_path):
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert [(out / ("ok%d" % k)).read_text() for k in range(2)] == ["1", "1"]
+
+
+def test_slab_engine_observables_single_rank(ig):
+    """SlabEngine with one rank: whole-lattice observables are the context's own."""
+    import torch
+    from ising_gpu_b200.slab import SlabEngine
+    X, Y = 4096, 64
+    se = SlabEngine(X, Y, TC, 463463564571, rank=0, world=1, device=0)
+    se.init_lattice()
+    se.sweeps(3)
+    torch.cuda.synchronize()
+    with ig.IsingEngine(X, Y, temp=TC) as one:
+        one.init_lattice()
+        one.sweeps(3)
+        assert np.array_equal(se.correlation(8), one.correlation(8))
+        assert se.bond_sum() == one.bond_sum() and se.energy_per_site() == one.energy_per_site()
+    se.close()
+
+
+@pytest.mark.parametrize("nranks,overlap", [(2, 1), (2, 2), (4, 2)])
+def test_whole_lattice_observables_across_processes(ig, tmp_path, nranks, overlap):
+    """torchrun, N ranks (NCCL halo / fused push): SlabEngine.correlation and .bond_sum of the lattice spread over the
+    processes == ising_correlation / ising_bond_sum of one context holding the stacked lattice (the reference's -c
+    covers all devices, optimized/main.cu:1072-1138), on every rank; the run goes on bit-exactly afterwards."""
+    if _ngpu() < nranks:
+        pytest.skip("needs %d GPUs" % nranks)
+    X, Y, sweeps, ncorr = 4096, 96, 4, 12
+    out = tmp_path / "obs"
+    out.mkdir()
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=%d" % nranks, "--master-addr",
+           "127.0.0.1", "--master-port", "29535", os.path.join(ROOT, "tests", "slab_obs_worker.py"), str(X), str(Y),
+           str(sweeps), str(TC), str(overlap), str(ncorr), str(out)]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    got = [np.load(out / ("r%d.npz" % k)) for k in range(nranks)]
+    with ig.IsingEngine(X, Y * nranks, temp=TC) as one:
+        one.init_lattice()
+        one.sweeps(sweeps)
+        corr, bs, e = one.correlation(ncorr), one.bond_sum(), one.energy_per_site()
+        one.sweeps(1)
+        ob, ow = one.export_bits()
+    for g in got:
+        assert np.array_equal(g["corr"], corr)
+        assert int(g["bond_sum"]) == bs and float(g["energy"]) == e
+    assert np.array_equal(np.vstack([g["b"] for g in got]), ob) and np.array_equal(np.vstack([g["w"] for g in got]), ow)

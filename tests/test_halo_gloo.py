@@ -87,3 +87,50 @@ def test_slabs_plus_halo_equal_full_lattice(oracle, world):
 def test_halo_is_noop_for_single_slab():
     from ising_gpu_b200.slab import HaloExchange
     assert HaloExchange(0, 1).start(None, 0) == []
+
+
+def _gather_worker(rank, world, port, root, q):
+    sys.path.insert(0, ROOT)
+    from ising_gpu_b200.slab import gather_slabs
+    dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world)
+    try:
+        rng = np.random.default_rng(100 + rank)
+        b = rng.integers(0, 2**32, size=(16, 32), dtype=np.uint32)
+        w = rng.integers(0, 2**32, size=(16, 32), dtype=np.uint32)
+        B, W = gather_slabs(b, w, rank, world, root=root)
+        q.put((rank, b, w, B, W))
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,root", [(2, 0), (3, 1)])
+def test_gather_slabs_stacks_the_ranks_in_slab_order(world, root):
+    """What SlabEngine.correlation feeds to the whole-lattice context: rank r's planes are rows [r*Y, (r+1)*Y) of the
+    arrays the root gets (optimized/main.cu:1542-1545), nobody else gets anything."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_gather_worker, args=(r, world, port, root, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = {}
+    for _ in range(world):
+        r, b, w, B, W = q.get(timeout=120)
+        got[r] = (b, w, B, W)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for r in range(world):
+        if r != root:
+            assert got[r][2] is None and got[r][3] is None
+    assert got[root][2].dtype == np.uint32
+    assert np.array_equal(got[root][2], np.vstack([got[r][0] for r in range(world)]))
+    assert np.array_equal(got[root][3], np.vstack([got[r][1] for r in range(world)]))
+
+
+def test_gather_slabs_single_rank_is_identity():
+    from ising_gpu_b200.slab import gather_slabs
+    b = np.arange(64, dtype=np.uint32).reshape(2, 32)
+    B, W = gather_slabs(b, b + 1, 0, 1)
+    assert np.array_equal(B, b) and np.array_equal(W, b + 1)
